@@ -1,0 +1,337 @@
+// g3d_capi.cu -- the extern "C" surface declared in include/g3d.h.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "g3d_internal.h"
+
+namespace g3d {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return G3D_ERR_CUDA;
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace g3d
+
+using namespace g3d;
+
+struct g3d_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+namespace {
+
+// grow-only device arena; returns nullptr on failure (error already set)
+char* arena_reserve(g3d_context* c, size_t bytes)
+{
+    if (bytes <= c->arena_bytes) return c->arena;
+    if (c->arena) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->arena);
+        c->arena = nullptr;
+        c->arena_bytes = 0;
+    }
+    size_t want = align_up(bytes + bytes / 8, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc((void**)&c->arena, want);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc(arena)"); return nullptr; }
+    c->arena_bytes = want;
+    return c->arena;
+}
+
+struct Carver {
+    char* base; size_t off = 0;
+    explicit Carver(char* b) : base(b) {}
+    template <class T> T* take(size_t count) {
+        size_t o = off; off = align_up(off + count * sizeof(T), 256);
+        return base ? reinterpret_cast<T*>(base + o) : nullptr;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int g3d_version(void) { return 100; }
+
+const char* g3d_last_error(void) { return g_err; }
+
+int g3d_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+size_t g3d_tdf_workspace_bytes(int32_t n_mesh, int64_t total_verts, int64_t total_tris, const g3d_tdf_params* params)
+{
+    (void)total_verts;
+    if (!params || n_mesh < 0 || total_tris < 0) return 0;
+    return params->mode == G3D_MODE_EXACT ? tdf_exact_workspace_bytes(n_mesh, total_tris, *params)
+                                          : tdf_faithful_workspace_bytes(n_mesh, total_tris, *params);
+}
+
+int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_verts, const uint32_t* tris,
+                  const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params* params,
+                  const g3d_tdf_outputs* out, void* workspace, size_t workspace_bytes, void* cuda_stream)
+{
+    if (!params || !out) { set_error("tdf: params/out is NULL"); return G3D_ERR_INVALID; }
+    if (n_mesh > 0 && (!vert_off || !tri_off)) { set_error("tdf: offsets are NULL"); return G3D_ERR_INVALID; }
+    if ((total_verts > 0 && !verts) || (total_tris > 0 && !tris)) { set_error("tdf: verts/tris are NULL"); return G3D_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (params->mode == G3D_MODE_FAITHFUL)
+        return tdf_faithful_launch(verts, vert_off, total_verts, tris, tri_off, total_tris, n_mesh, *params, *out,
+                                   workspace, workspace_bytes, s);
+    if (params->mode == G3D_MODE_EXACT)
+        return tdf_exact_launch(verts, vert_off, total_verts, tris, tri_off, total_tris, n_mesh, *params, *out,
+                                workspace, workspace_bytes, s);
+    set_error("tdf: unknown mode %d", params->mode);
+    return G3D_ERR_INVALID;
+}
+
+int g3d_tdf_from_sdf(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog, void* cuda_stream)
+{
+    return tdf_from_sdf_launch(sdf, n, trunc, tdf, tdflog, (cudaStream_t)cuda_stream);
+}
+
+int g3d_unpack_occ(const uint32_t* occ_bits, int64_t n_bits, float* occ_f32, void* cuda_stream)
+{
+    return unpack_occ_launch(occ_bits, n_bits, occ_f32, (cudaStream_t)cuda_stream);
+}
+
+int g3d_raycast_batch(const uint8_t* depth, const float* pose, int32_t n_view, int32_t H, int32_t W, float focal,
+                      float cx, float cy, int32_t clamp_max, int32_t dim, uint32_t* occ_bits, float* occ_f32,
+                      int64_t* index_map, void* cuda_stream)
+{
+    return raycast_launch(depth, pose, n_view, H, W, focal, cx, cy, clamp_max, dim, occ_bits, occ_f32, index_map,
+                          (cudaStream_t)cuda_stream);
+}
+
+// ---------------------------------------------------------------- context ----
+int g3d_context_create(int32_t device, g3d_context** ctx)
+{
+    if (!ctx) { set_error("ctx is NULL"); return G3D_ERR_INVALID; }
+    *ctx = nullptr;
+    int n = 0;
+    G3D_CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return G3D_ERR_INVALID; }
+    G3D_CUDA_TRY(cudaSetDevice(device));
+    g3d_context* c = new g3d_context();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    *ctx = c;
+    return G3D_OK;
+}
+
+void g3d_context_destroy(g3d_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->arena) cudaFree(c->arena);
+    delete c;
+}
+
+size_t g3d_context_arena_bytes(const g3d_context* c) { return c ? c->arena_bytes : 0; }
+
+int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_off, const uint32_t* tris,
+                       const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
+                       const g3d_tdf_outputs* out)
+{
+    if (!c || !params || !out) { set_error("tdf_host: NULL argument"); return G3D_ERR_INVALID; }
+    if (n_mesh < 0) { set_error("tdf_host: n_mesh < 0"); return G3D_ERR_INVALID; }
+    if (n_mesh == 0) return G3D_OK;
+    if (!vert_off || !tri_off) { set_error("tdf_host: offsets are NULL"); return G3D_ERR_INVALID; }
+    const int64_t nv = vert_off[n_mesh], nt = tri_off[n_mesh];
+    if (nv < 0 || nt < 0 || (nv > 0 && !verts) || (nt > 0 && !tris)) { set_error("tdf_host: bad mesh arrays"); return G3D_ERR_INVALID; }
+    for (int m = 0; m < n_mesh; ++m)
+        if (vert_off[m + 1] < vert_off[m] || tri_off[m + 1] < tri_off[m]) { set_error("tdf_host: offsets not monotone"); return G3D_ERR_INVALID; }
+    G3D_CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t nvox = (int64_t)params->ni * params->nj * params->nk, pw = (nvox + 31) / 32;
+    const size_t ws_bytes = g3d_tdf_workspace_bytes(n_mesh, nv, nt, params);
+
+    auto layout = [&](char* base, g3d_tdf_outputs& d, float*& dv, int64_t*& dvo, uint32_t*& dt, int64_t*& dto, void*& ws) {
+        Carver k(base);
+        dv = k.take<float>((size_t)nv * 3);
+        dvo = k.take<int64_t>((size_t)n_mesh + 1);
+        dt = k.take<uint32_t>((size_t)nt * 3);
+        dto = k.take<int64_t>((size_t)n_mesh + 1);
+        d.sdf = out->sdf ? k.take<float>((size_t)n_mesh * nvox) : nullptr;
+        d.tdf = out->tdf ? k.take<float>((size_t)n_mesh * nvox) : nullptr;
+        d.tdflog = out->tdflog ? k.take<float>((size_t)n_mesh * nvox) : nullptr;
+        d.occ_bits = out->occ_bits ? k.take<uint32_t>((size_t)n_mesh * pw) : nullptr;
+        d.occ_f32 = out->occ_f32 ? k.take<float>((size_t)n_mesh * nvox) : nullptr;
+        d.closest_tri = out->closest_tri ? k.take<int32_t>((size_t)n_mesh * nvox) : nullptr;
+        d.status = out->status ? k.take<int32_t>((size_t)n_mesh) : nullptr;
+        ws = k.take<char>(ws_bytes);
+        return k.off;
+    };
+    g3d_tdf_outputs d{};
+    float* dv; int64_t* dvo; uint32_t* dt; int64_t* dto; void* ws;
+    size_t need = layout(nullptr, d, dv, dvo, dt, dto, ws);
+    char* base = arena_reserve(c, need);
+    if (!base) return G3D_ERR_CUDA;
+    layout(base, d, dv, dvo, dt, dto, ws);
+
+    cudaStream_t s = c->stream;
+    if (nv) G3D_CUDA_TRY(cudaMemcpyAsync(dv, verts, (size_t)nv * 12, cudaMemcpyHostToDevice, s));
+    if (nt) G3D_CUDA_TRY(cudaMemcpyAsync(dt, tris, (size_t)nt * 12, cudaMemcpyHostToDevice, s));
+    G3D_CUDA_TRY(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, s));
+    G3D_CUDA_TRY(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, s));
+    int rc = g3d_tdf_batch(dv, dvo, nv, dt, dto, nt, n_mesh, params, &d, ws, ws_bytes, s);
+    if (rc != G3D_OK) return rc;
+    const size_t gb = (size_t)n_mesh * nvox * 4;
+    if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf, d.sdf, gb, cudaMemcpyDeviceToHost, s));
+    if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf, d.tdf, gb, cudaMemcpyDeviceToHost, s));
+    if (out->tdflog) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdflog, d.tdflog, gb, cudaMemcpyDeviceToHost, s));
+    if (out->occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_bits, d.occ_bits, (size_t)n_mesh * pw * 4, cudaMemcpyDeviceToHost, s));
+    if (out->occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_f32, d.occ_f32, gb, cudaMemcpyDeviceToHost, s));
+    if (out->closest_tri) G3D_CUDA_TRY(cudaMemcpyAsync(out->closest_tri, d.closest_tri, gb, cudaMemcpyDeviceToHost, s));
+    if (out->status) G3D_CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, s));
+    G3D_CUDA_TRY(cudaStreamSynchronize(s));
+    return G3D_OK;
+}
+
+int g3d_raycast_batch_host(g3d_context* c, const uint8_t* depth, const float* pose, int32_t n_view, int32_t H,
+                           int32_t W, float focal, float cx, float cy, int32_t clamp_max, int32_t dim,
+                           uint32_t* occ_bits, float* occ_f32, int64_t* index_map)
+{
+    if (!c) { set_error("raycast_host: ctx is NULL"); return G3D_ERR_INVALID; }
+    if (n_view < 0 || H < 1 || W < 1 || dim < 1) { set_error("raycast_host: bad sizes"); return G3D_ERR_INVALID; }
+    if (n_view == 0) return G3D_OK;
+    if (!depth || !pose) { set_error("raycast_host: null input"); return G3D_ERR_INVALID; }
+    G3D_CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t nvox = (int64_t)dim * dim * dim, pw = (nvox + 31) / 32;
+    const size_t img = (size_t)n_view * H * W;
+    auto layout = [&](char* base, uint8_t*& dd, float*& dp, uint32_t*& db, float*& df, int64_t*& di) {
+        Carver k(base);
+        dd = k.take<uint8_t>(img);
+        dp = k.take<float>((size_t)n_view * 16);
+        db = occ_bits ? k.take<uint32_t>((size_t)n_view * pw) : nullptr;
+        df = occ_f32 ? k.take<float>((size_t)n_view * nvox) : nullptr;
+        di = index_map ? k.take<int64_t>((size_t)n_view * 4 * nvox) : nullptr;
+        return k.off;
+    };
+    uint8_t* dd; float* dp; uint32_t* db; float* df; int64_t* di;
+    size_t need = layout(nullptr, dd, dp, db, df, di);
+    char* base = arena_reserve(c, need);
+    if (!base) return G3D_ERR_CUDA;
+    layout(base, dd, dp, db, df, di);
+    cudaStream_t s = c->stream;
+    G3D_CUDA_TRY(cudaMemcpyAsync(dd, depth, img, cudaMemcpyHostToDevice, s));
+    G3D_CUDA_TRY(cudaMemcpyAsync(dp, pose, (size_t)n_view * 64, cudaMemcpyHostToDevice, s));
+    int rc = g3d_raycast_batch(dd, dp, n_view, H, W, focal, cx, cy, clamp_max, dim, db, df, di, s);
+    if (rc != G3D_OK) return rc;
+    if (occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(occ_bits, db, (size_t)n_view * pw * 4, cudaMemcpyDeviceToHost, s));
+    if (occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(occ_f32, df, (size_t)n_view * nvox * 4, cudaMemcpyDeviceToHost, s));
+    if (index_map) G3D_CUDA_TRY(cudaMemcpyAsync(index_map, di, (size_t)n_view * 4 * nvox * 8, cudaMemcpyDeviceToHost, s));
+    G3D_CUDA_TRY(cudaStreamSynchronize(s));
+    return G3D_OK;
+}
+
+// ----------------------------------------------------------- dfgen driver ----
+int g3d_dfgen_geometry(int32_t dim, int32_t padding, int32_t is_unit_cube, const float* bbox_min,
+                       const float* bbox_max, g3d_tdf_params* p, float* g2w)
+{
+    if (!p || !g2w) { set_error("dfgen_geometry: NULL output"); return G3D_ERR_INVALID; }
+    if (dim - 2 * padding <= 0 || dim < 1) { set_error("dfgen_geometry: dim - 2*padding must be positive"); return G3D_ERR_INVALID; }
+    if (!is_unit_cube && (!bbox_min || !bbox_max)) { set_error("dfgen_geometry: bbox required"); return G3D_ERR_INVALID; }
+    // main.cpp:57: float dx = 1.0/(dim - 2*padding)  (double quotient rounded to float)
+    const float dx = (float)(1.0 / (double)(dim - 2 * padding));
+    int sizes[3];
+    for (int a = 0; a < 3; ++a) {
+        float lo = is_unit_cube ? -0.5f : bbox_min[a];             // main.cpp:82-85
+        float hi = is_unit_cube ? 0.5f : bbox_max[a];
+        const float pad = (float)padding * dx;                     // main.cpp:91-93
+        lo -= pad;
+        hi += pad;
+        const float q = (hi - lo) / dx;                            // main.cpp:94, Vec3ui(...) truncates
+        sizes[a] = (q >= 0.f && q < 2147483648.f) ? (int)(unsigned int)q : -1;
+        p->origin[a] = lo;
+    }
+    p->ni = sizes[0]; p->nj = sizes[1]; p->nk = sizes[2];
+    p->dx = dx;
+    p->out_scale = (float)dim;                                     // main.cpp:119
+    p->exact_band = 1;
+    const float dfix = (float)(1.0 / (double)dim);                 // main.cpp:107
+    const float tr = padding != 0 ? (-0.5f - dfix) : -0.5f;        // main.cpp:110-113
+    memset(g2w, 0, 16 * sizeof(float));
+    g2w[0] = g2w[5] = g2w[10] = dx;
+    g2w[3] = g2w[7] = g2w[11] = tr;
+    g2w[15] = 1.f;
+    if (sizes[0] != dim || sizes[1] != dim || sizes[2] != dim) {
+        set_error("dfgen: grid %dx%dx%d != dim %d (the reference asserts here, main.cpp:102)", sizes[0], sizes[1], sizes[2], dim);
+        return G3D_ERR_ASSERT;
+    }
+    return G3D_OK;
+}
+
+int g3d_write_df(const char* path, const int32_t* dims, float res, const float* g2w, const float* sdf)
+{
+    if (!path || !dims || !g2w || !sdf) { set_error("write_df: NULL argument"); return G3D_ERR_INVALID; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("write_df: cannot open %s", path); return G3D_ERR_IO; }
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    bool ok = fwrite(dims, 4, 3, f) == 3 && fwrite(&res, 4, 1, f) == 1 && fwrite(g2w, 4, 16, f) == 16 &&
+              fwrite(sdf, 4, n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { set_error("write_df: short write to %s", path); return G3D_ERR_IO; }
+    return G3D_OK;
+}
+
+int g3d_read_df(const char* path, int32_t* dims, float* res, float* g2w, float* sdf, int64_t capacity)
+{
+    if (!path || !dims) { set_error("read_df: NULL argument"); return G3D_ERR_INVALID; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("read_df: cannot open %s", path); return G3D_ERR_IO; }
+    float r = 0, m[16];
+    bool ok = fread(dims, 4, 3, f) == 3 && fread(&r, 4, 1, f) == 1 && fread(m, 4, 16, f) == 16;
+    if (ok && res) *res = r;
+    if (ok && g2w) memcpy(g2w, m, sizeof m);
+    if (ok && sdf) {
+        int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+        if (dims[0] < 0 || dims[1] < 0 || dims[2] < 0 || n > capacity) {
+            fclose(f);
+            set_error("read_df: %s holds %lld values, capacity %lld", path, (long long)n, (long long)capacity);
+            return G3D_ERR_INVALID;
+        }
+        ok = fread(sdf, 4, (size_t)n, f) == (size_t)n;
+    }
+    fclose(f);
+    if (!ok) { set_error("read_df: short read from %s", path); return G3D_ERR_IO; }
+    return G3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// g3d_internal.h -- declarations shared by the translation units of libg3d_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/g3d.h"
+
+namespace g3d {
+
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+#define G3D_CUDA_TRY(expr)                                          \
+    do {                                                            \
+        cudaError_t e__ = (expr);                                   \
+        if (e__ != cudaSuccess) return g3d::cuda_fail(e__, #expr);  \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- faithful TDF (g3d_tdf.cu)
+size_t tdf_faithful_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
+int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
+                        const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
+                        int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
+                        void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// ---- exact (brute-force, truncation-culled) TDF (g3d_tdf_exact.cu)
+size_t tdf_exact_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
+int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
+                     const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
+                     int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
+                     void* ws, size_t ws_bytes, cudaStream_t stream);
+
+int tdf_from_sdf_launch(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog,
+                        cudaStream_t stream);
+int unpack_occ_launch(const uint32_t* bits, int64_t n_bits, float* out, cudaStream_t stream);
+
+// ---- raycast (g3d_raycast.cu)
+int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int32_t H, int32_t W,
+                   float focal, float cx, float cy, int32_t clamp_max, int32_t dim,
+                   uint32_t* occ_bits, float* occ_f32, int64_t* index_map, cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace g3d

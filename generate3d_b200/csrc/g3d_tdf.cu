@@ -1,0 +1,519 @@
+// g3d_tdf.cu -- reference-faithful distance field on sm_100a.
+//
+// Reproduces make_level_set3 (src/dfgen/makelevelset3.cpp:118-183) bit for bit,
+// for a batch of meshes, with the sequential loops re-expressed as
+// order-independent parallel steps:
+//
+//  tdf_prep      one thread / triangle: gathers the three vertices into a
+//                48-byte record, computes the double-precision grid coordinates,
+//                the band box [int(min)-b, int(max)+b+1] (cpp:131-137) and the
+//                x-ray intersection counts (cpp:147-160). Only the PARITY of the
+//                counts is ever used (cpp:178), so they are kept as XOR-ed bits.
+//  tdf_init      one warp / triangle over its band box. The reference's serial
+//                "if (d < phi) {phi = d; closest = t}" over t = 0..T-1 ends at
+//                (min d, lowest t attaining it); atomicMin on the 64-bit key
+//                (float_bits(d) << 32 | t) is exactly that, in any order.
+//  tdf_sweep     one CTA / mesh, the 2 x 8 Gauss-Seidel sweeps (cpp:57-80,
+//                163-172). Within one sweep node (a,b,c) (sweep-relative) reads
+//                only nodes of smaller a+b+c, so the nodes of one anti-diagonal
+//                level are independent: 16 x (ni+nj+nk-5) block-synchronous
+//                wavefront steps instead of 16 x (n-1)^3 serial ones. Each node
+//                re-tests its 7 upwind neighbours in the reference's order
+//                with strict <.
+//  tdf_finalize  one warp / grid row: running parity along i (cpp:174-182),
+//                x out_scale (main.cpp:119), and the fused epilogues the
+//                pipeline applies later on the CPU: |sdf| <= 1 occupancy
+//                (vox2mesh/main.cpp:92), clamp at trunc (dataset_loader.py:
+//                137-139), sign*log(|x|+1) (losses.py:7-11).
+//
+// HBM layout (workspace): tri records [T_total] 48 B; band boxes [T_total] 16 B;
+// keys u64 [n_mesh, nk, nj, ni] (hi = phi bits, lo = closest_tri); parity bits
+// u32 [n_mesh, ceil(nvox/32)]; sweep order table (shared by all meshes).
+#include <limits.h>
+
+#include "g3d_internal.h"
+#include "g3d_ptd.cuh"
+
+namespace g3d {
+
+namespace {
+
+typedef unsigned long long u64;
+
+struct TdfWs {
+    float4*   tri;          // 3 x float4 per triangle: x1, x2, x3 (w unused)
+    int4*     box;          // i0|i1<<16, j0|j1<<16, k0|k1<<16, mesh
+    u64*      key;
+    uint32_t* parity;
+    uint32_t* order;        // packed a | b<<10 | c<<20, grouped by level
+    int32_t*  level_start;  // [nlev + 1]
+    size_t    bytes;
+};
+
+__host__ __device__ inline int64_t nvox_of(const g3d_tdf_params& p) { return (int64_t)p.ni * p.nj * p.nk; }
+inline int nlev_of(const g3d_tdf_params& p)
+{
+    int l = (p.ni - 2) + (p.nj - 2) + (p.nk - 2) + 1;
+    return (p.ni < 2 || p.nj < 2 || p.nk < 2) ? 0 : l;
+}
+
+TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
+{
+    TdfWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+    int64_t nvox = nvox_of(p);
+    int64_t pw = (nvox + 31) / 32;
+    int64_t nsweep = (int64_t)(p.ni - 1) * (p.nj - 1) * (p.nk - 1);
+    if (nsweep < 0) nsweep = 0;
+    w.tri = (float4*)take((size_t)total_tris * 48);
+    w.box = (int4*)take((size_t)total_tris * 16);
+    w.key = (u64*)take((size_t)n_mesh * nvox * 8);
+    w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
+    w.order = (uint32_t*)take((size_t)nsweep * 4);
+    w.level_start = (int32_t*)take((size_t)(nlev_of(p) + 2) * 4);
+    w.bytes = off;
+    return w;
+}
+
+// ------------------------------------------------------------------ fill ----
+__global__ void tdf_fill_kernel(u64* key, int64_t n_key, u64 init, uint32_t* parity, int64_t n_par,
+                                int32_t* status, int32_t n_mesh, uint32_t* occ_bits, int64_t n_occ)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < n_key; i += stride) key[i] = init;
+    for (int64_t i = t0; i < n_par; i += stride) parity[i] = 0u;
+    if (occ_bits) for (int64_t i = t0; i < n_occ; i += stride) occ_bits[i] = 0u;
+    if (status) for (int64_t i = t0; i < n_mesh; i += stride) status[i] = 0;
+}
+
+// ------------------------------------------------------------------ prep ----
+__device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ int clampi(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
+
+// makelevelset3.cpp:84-94, without FMA contraction
+__device__ __forceinline__ int orientation2d(double x1, double y1, double x2, double y2, double& area2)
+{
+    area2 = __dsub_rn(__dmul_rn(y1, x2), __dmul_rn(x1, y2));
+    if (area2 > 0) return 1;
+    if (area2 < 0) return -1;
+    if (y2 > y1) return 1;
+    if (y2 < y1) return -1;
+    if (x1 > x2) return 1;
+    if (x1 < x2) return -1;
+    return 0;
+}
+
+// makelevelset3.cpp:98-116
+__device__ __forceinline__ bool point_in_triangle_2d(double x0, double y0, double x1, double y1,
+                                                     double x2, double y2, double x3, double y3,
+                                                     double& a, double& b, double& c)
+{
+    x1 = __dsub_rn(x1, x0); x2 = __dsub_rn(x2, x0); x3 = __dsub_rn(x3, x0);
+    y1 = __dsub_rn(y1, y0); y2 = __dsub_rn(y2, y0); y3 = __dsub_rn(y3, y0);
+    int sa = orientation2d(x2, y2, x3, y3, a);
+    if (sa == 0) return false;
+    int sb = orientation2d(x3, y3, x1, y1, b);
+    if (sb != sa) return false;
+    int sc = orientation2d(x1, y1, x2, y2, c);
+    if (sc != sa) return false;
+    double sum = __dadd_rn(__dadd_rn(a, b), c);
+    a = __ddiv_rn(a, sum);
+    b = __ddiv_rn(b, sum);
+    c = __ddiv_rn(c, sum);
+    return true;
+}
+
+__device__ __forceinline__ int mesh_of(const int64_t* off, int n_mesh, int64_t t)
+{
+    int lo = 0, hi = n_mesh;                       // off[lo] <= t < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ vert_off,
+                const uint32_t* __restrict__ tris, const int64_t* __restrict__ tri_off,
+                int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
+                int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_tris) return;
+    int m = mesh_of(tri_off, n_mesh, t);
+    int64_t v0 = vert_off[m], nv = vert_off[m + 1] - v0;
+    uint32_t ip = tris[3 * t], iq = tris[3 * t + 1], ir = tris[3 * t + 2];
+    if (ip >= nv || iq >= nv || ir >= nv) {
+        // undefined behaviour in the reference (out-of-bounds read); flag the mesh
+        // and neutralise the triangle: NaN vertices never win a `<` and an empty box
+        if (status) atomicOr(status + m, G3D_MESH_BAD_INDEX);
+        float qnan = __int_as_float(0x7fc00000);
+        tri_out[3 * t] = tri_out[3 * t + 1] = tri_out[3 * t + 2] = make_float4(qnan, qnan, qnan, 0.f);
+        box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
+        return;
+    }
+    const float* pp = verts + 3 * (v0 + ip);
+    const float* pq = verts + 3 * (v0 + iq);
+    const float* pr = verts + 3 * (v0 + ir);
+    float xp[3] = { pp[0], pp[1], pp[2] }, xq[3] = { pq[0], pq[1], pq[2] }, xr[3] = { pr[0], pr[1], pr[2] };
+    tri_out[3 * t]     = make_float4(xp[0], xp[1], xp[2], 0.f);
+    tri_out[3 * t + 1] = make_float4(xq[0], xq[1], xq[2], 0.f);
+    tri_out[3 * t + 2] = make_float4(xr[0], xr[1], xr[2], 0.f);
+
+    const int dims[3] = { P.ni, P.nj, P.nk };
+    double fp[3], fq[3], fr[3];
+    int lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {                  // cpp:131-137
+        double o = (double)P.origin[a], h = (double)P.dx;
+        fp[a] = __ddiv_rn(__dsub_rn((double)xp[a], o), h);
+        fq[a] = __ddiv_rn(__dsub_rn((double)xq[a], o), h);
+        fr[a] = __ddiv_rn(__dsub_rn((double)xr[a], o), h);
+        double mn = dmin(fp[a], dmin(fq[a], fr[a])), mx = dmax(fp[a], dmax(fq[a], fr[a]));
+        long long l = (long long)x86_d2i(mn) - P.exact_band;
+        long long u = (long long)x86_d2i(mx) + P.exact_band + 1;
+        lo[a] = (int)(l < 0 ? 0 : (l > dims[a] - 1 ? dims[a] - 1 : l));
+        hi[a] = (int)(u < 0 ? 0 : (u > dims[a] - 1 ? dims[a] - 1 : u));
+    }
+    box_out[t] = make_int4(lo[0] | (hi[0] << 16), lo[1] | (hi[1] << 16), lo[2] | (hi[2] << 16), m);
+
+    // cpp:147-160: x-ray intersection parity
+    int j0 = clampi(x86_d2i(ceil(dmin(fp[1], dmin(fq[1], fr[1])))), 0, P.nj - 1);
+    int j1 = clampi(x86_d2i(floor(dmax(fp[1], dmax(fq[1], fr[1])))), 0, P.nj - 1);
+    int k0 = clampi(x86_d2i(ceil(dmin(fp[2], dmin(fq[2], fr[2])))), 0, P.nk - 1);
+    int k1 = clampi(x86_d2i(floor(dmax(fp[2], dmax(fq[2], fr[2])))), 0, P.nk - 1);
+    int64_t nvox = nvox_of(P);
+    uint32_t* par = parity + (int64_t)m * ((nvox + 31) / 32);
+    for (int k = k0; k <= k1; ++k)
+        for (int j = j0; j <= j1; ++j) {
+            double a, b, c;
+            if (point_in_triangle_2d((double)j, (double)k, fp[1], fp[2], fq[1], fq[2], fr[1], fr[2], a, b, c)) {
+                double fi = __dadd_rn(__dadd_rn(__dmul_rn(a, fp[0]), __dmul_rn(b, fq[0])), __dmul_rn(c, fr[0]));
+                int iv = x86_d2i(ceil(fi));
+                int bin = iv < 0 ? 0 : iv;
+                if (bin < P.ni) {
+                    int64_t idx = bin + (int64_t)P.ni * (j + (int64_t)P.nj * k);
+                    atomicXor(par + (idx >> 5), 1u << (idx & 31));
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------ init ----
+__device__ __forceinline__ V3 node_pos(int i, int j, int k, const g3d_tdf_params& P)
+{
+    // Vec3f gx(i*dx+origin[0], ...) (cpp:139): int -> float, one mul, one add
+    return { add(mul((float)i, P.dx), P.origin[0]), add(mul((float)j, P.dx), P.origin[1]),
+             add(mul((float)k, P.dx), P.origin[2]) };
+}
+
+__global__ void __launch_bounds__(256)
+tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
+                const int64_t* __restrict__ tri_off, int64_t total_tris, g3d_tdf_params P,
+                u64* __restrict__ key, float far)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t nvox = nvox_of(P);
+    for (int64_t t = warp; t < total_tris; t += nwarp) {
+        int4 b = __ldg(box + t);
+        int i0 = b.x & 0xffff, i1 = b.x >> 16, j0 = b.y & 0xffff, j1 = b.y >> 16, k0 = b.z & 0xffff, k1 = b.z >> 16;
+        int bi = i1 - i0 + 1, bj = j1 - j0 + 1, bk = k1 - k0 + 1;
+        if (bi <= 0 || bj <= 0 || bk <= 0) continue;
+        float4 a1 = __ldg(tri + 3 * t), a2 = __ldg(tri + 3 * t + 1), a3 = __ldg(tri + 3 * t + 2);
+        V3 x1 = { a1.x, a1.y, a1.z }, x2 = { a2.x, a2.y, a2.z }, x3 = { a3.x, a3.y, a3.z };
+        uint32_t tl = (uint32_t)(t - tri_off[b.w]);
+        u64* K = key + (int64_t)b.w * nvox;
+        int n = bi * bj * bk;
+        for (int q = lane; q < n; q += 32) {
+            int i = i0 + q % bi, r = q / bi;
+            int j = j0 + r % bj, k = k0 + r / bj;
+            float d = point_triangle_distance(node_pos(i, j, k, P), x1, x2, x3);
+            u64* kp = K + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k));
+            float cur = __uint_as_float((uint32_t)(*(volatile u64*)kp >> 32));
+            // d < far mirrors the very first `d < phi`; d <= cur lets an equal
+            // distance with a LOWER triangle index through, as the serial loop would
+            if (d < far && d <= cur) atomicMin(kp, ((u64)__float_as_uint(d) << 32) | tl);
+        }
+    }
+}
+
+// ----------------------------------------------------------- sweep order ----
+// Nodes of the sweep lattice (ni-1)(nj-1)(nk-1) grouped by level a+b+c.
+__global__ void __launch_bounds__(1024)
+tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order, int32_t* __restrict__ level_start)
+{
+    extern __shared__ int32_t s_cnt[];             // [nlev + 1]
+    for (int l = threadIdx.x; l <= nlev; l += blockDim.x) s_cnt[l] = 0;
+    __syncthreads();
+    int64_t n = (int64_t)na * nb * nc;
+    for (int64_t q = threadIdx.x; q < n; q += blockDim.x) {
+        int a = (int)(q % na), r = (int)(q / na);
+        atomicAdd(&s_cnt[a + r % nb + r / nb], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int l = 0; l < nlev; ++l) { int c = s_cnt[l]; s_cnt[l] = acc; level_start[l] = acc; acc += c; }
+        level_start[nlev] = acc;
+    }
+    __syncthreads();
+    for (int64_t q = threadIdx.x; q < n; q += blockDim.x) {
+        int a = (int)(q % na), r = (int)(q / na);
+        int b = r % nb, c = r / nb;
+        int pos = atomicAdd(&s_cnt[a + b + c], 1);
+        order[pos] = (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)c << 20);
+    }
+}
+
+// ----------------------------------------------------------------- sweep ----
+template <int NT>
+__global__ void __launch_bounds__(NT)
+tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
+                 const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
+                 g3d_tdf_params P)
+{
+    extern __shared__ int32_t s_lev[];             // [nlev + 1]
+    for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
+    __syncthreads();
+    const int mesh = blockIdx.x;
+    const int64_t nvox = nvox_of(P);
+    u64* K = key + (int64_t)mesh * nvox;
+    const int* Klo = (const int*)K;                // low word of each key = closest_tri
+    const float4* T = tri + 3 * tri_off[mesh];
+    const int ni = P.ni, nj = P.nj, nk = P.nk;
+    const int sj = ni, sk = ni * nj;
+
+    for (int s = 0; s < 16; ++s) {
+        // cpp:163-172 sweep directions, pass 0 then pass 1
+        const int q8 = s & 7;
+        const int di = (q8 & 1) ? -1 : 1;
+        const int dj = (q8 == 0 || q8 == 2 || q8 == 5 || q8 == 7) ? 1 : -1;
+        const int dk = (q8 == 0 || q8 == 3 || q8 == 4 || q8 == 7) ? 1 : -1;
+        const int oi = di, oj = dj * sj, ok = dk * sk;
+        for (int L = 0; L < nlev; ++L) {
+            const int beg = s_lev[L], end = s_lev[L + 1];
+            for (int q = beg + threadIdx.x; q < end; q += NT) {
+                uint32_t o = __ldg(order + q);
+                int a = o & 1023, b = (o >> 10) & 1023, c = o >> 20;
+                int i = di > 0 ? 1 + a : ni - 2 - a;
+                int j = dj > 0 ? 1 + b : nj - 2 - b;
+                int k = dk > 0 ? 1 + c : nk - 2 - c;
+                int n = i + sj * j + sk * k;
+                // the 7 upwind neighbours in the order of cpp:72-78
+                int c0 = Klo[2 * (n - oi)], c1 = Klo[2 * (n - oj)], c2 = Klo[2 * (n - oi - oj)],
+                    c3 = Klo[2 * (n - ok)], c4 = Klo[2 * (n - oi - ok)], c5 = Klo[2 * (n - oj - ok)],
+                    c6 = Klo[2 * (n - oi - oj - ok)];
+                u64 kv = K[n];
+                float phi = __uint_as_float((uint32_t)(kv >> 32));
+                int ct = (int)(uint32_t)kv;
+                // A candidate equal to the node's own triangle, or to an earlier
+                // candidate, re-evaluates to a distance that cannot pass the strict
+                // `<` (it equals or exceeds the current phi): skip it.
+                uint32_t need = 0;
+                need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
+                need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
+                need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
+                need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
+                need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
+                need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
+                need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                if (need) {
+                    V3 gx = node_pos(i, j, k, P);
+                    bool changed = false;
+#pragma unroll 1
+                    for (int r = 0; r < 7; ++r) {
+                        int t = c0;
+                        c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = c6;
+                        if (need & 1u) {
+                            float4 a1 = __ldg(T + 3 * t), a2 = __ldg(T + 3 * t + 1), a3 = __ldg(T + 3 * t + 2);
+                            float d = point_triangle_distance(gx, { a1.x, a1.y, a1.z }, { a2.x, a2.y, a2.z },
+                                                              { a3.x, a3.y, a3.z });
+                            if (d < phi) { phi = d; ct = t; changed = true; }
+                        }
+                        need >>= 1;
+                        if (!need) break;
+                    }
+                    if (changed) K[n] = ((u64)__float_as_uint(phi) << 32) | (uint32_t)ct;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// -------------------------------------------------------------- finalize ----
+__device__ __forceinline__ float log_transform(float x)
+{
+    // losses.py:7-11: sign(x) * log(|x| + 1)
+    float s = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+    return s * logf(fabsf(x) + 1.f);
+}
+
+__global__ void __launch_bounds__(256)
+tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ parity,
+                    const int64_t* __restrict__ vert_off, const int64_t* __restrict__ tri_off, int n_mesh,
+                    g3d_tdf_params P, g3d_tdf_outputs O, int signed_mode)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (mesh, k, j)
+    int64_t nrow = (int64_t)n_mesh * P.nk * P.nj;
+    if (row >= nrow) return;
+    int mesh = (int)(row / ((int64_t)P.nk * P.nj));
+    int64_t nvox = nvox_of(P), pw = (nvox + 31) / 32;
+    int64_t rbase = (row - (int64_t)mesh * P.nk * P.nj) * P.ni;           // node index of i = 0
+    const u64* K = key + (int64_t)mesh * nvox;
+    const uint32_t* par = parity + (int64_t)mesh * pw;
+    const bool aligned = (P.ni & 31) == 0;
+    if (O.status && lane == 0 && rbase == 0 &&
+        (tri_off[mesh + 1] == tri_off[mesh] || vert_off[mesh + 1] == vert_off[mesh]))
+        atomicOr(O.status + mesh, G3D_MESH_EMPTY);                          // LoaderMesh.h:83
+    int carry = 0;
+    for (int i0 = 0; i0 < P.ni; i0 += 32) {
+        int i = i0 + lane;
+        bool valid = i < P.ni;
+        int64_t idx = rbase + i;
+        uint32_t bit = valid ? ((par[idx >> 5] >> (idx & 31)) & 1u) : 0u;
+        uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        int incl = __popc(bal & (0xffffffffu >> (31 - lane)));
+        bool inside = signed_mode && (((carry + incl) & 1) != 0);           // cpp:176-181
+        carry += __popc(bal);
+        float sdf = 0.f;
+        int ct = -1;
+        if (valid) {
+            u64 kv = K[idx];
+            float phi = __uint_as_float((uint32_t)(kv >> 32));
+            ct = (int)(uint32_t)kv;
+            if (inside) phi = -phi;
+            sdf = mul(phi, P.out_scale);                                    // main.cpp:119
+        }
+        bool occ = valid && (fabsf(sdf) <= P.occ_thresh);                   // vox2mesh/main.cpp:92
+        uint32_t ob = __ballot_sync(0xffffffffu, occ);
+        int64_t g = (int64_t)mesh * nvox + idx;
+        if (valid) {
+            if (O.sdf) O.sdf[g] = sdf;
+            float tdf = sdf > P.trunc ? P.trunc : sdf;                      // dataset_loader.py:137-139
+            if (O.tdf) O.tdf[g] = tdf;
+            if (O.tdflog) O.tdflog[g] = log_transform(tdf);
+            if (O.occ_f32) O.occ_f32[g] = occ ? 1.f : 0.f;
+            if (O.closest_tri) O.closest_tri[g] = ct;
+        }
+        if (O.occ_bits) {
+            uint32_t* ow = O.occ_bits + (int64_t)mesh * pw;
+            if (aligned) { if (lane == 0) ow[idx >> 5] = ob; }
+            else if (occ) atomicOr(ow + (idx >> 5), 1u << (idx & 31));
+        }
+    }
+}
+
+__global__ void tdf_from_sdf_kernel(const float* __restrict__ sdf, int64_t n, float trunc,
+                                    float* __restrict__ tdf, float* __restrict__ tdflog)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float x = sdf[i];
+        x = x > trunc ? trunc : x;
+        if (tdf) tdf[i] = x;
+        if (tdflog) tdflog[i] = log_transform(x);
+    }
+}
+
+__global__ void unpack_occ_kernel(const uint32_t* __restrict__ bits, int64_t n_bits, float* __restrict__ out)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_bits; i += stride)
+        out[i] = ((bits[i >> 5] >> (i & 31)) & 1u) ? 1.f : 0.f;
+}
+
+int grid_for(int64_t n, int block, int max_blocks)
+{
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+}  // namespace
+
+size_t tdf_faithful_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
+{
+    return carve(nullptr, n_mesh, total_tris, p).bytes;
+}
+
+int tdf_validate(int32_t n_mesh, int64_t total_verts, int64_t total_tris, const g3d_tdf_params& p)
+{
+    if (n_mesh < 0 || total_verts < 0 || total_tris < 0) { set_error("negative size"); return G3D_ERR_INVALID; }
+    if (p.ni < 1 || p.nj < 1 || p.nk < 1 || p.ni > 1024 || p.nj > 1024 || p.nk > 1024) {
+        set_error("grid dims must be in [1, 1024], got %d %d %d", p.ni, p.nj, p.nk);
+        return G3D_ERR_INVALID;
+    }
+    if (nvox_of(p) >= (int64_t)INT_MAX) { set_error("grid too large"); return G3D_ERR_INVALID; }
+    if (!(p.dx > 0.f)) { set_error("dx must be positive"); return G3D_ERR_INVALID; }
+    if (p.exact_band < 0 || p.exact_band > 1024) { set_error("bad exact_band"); return G3D_ERR_INVALID; }
+    return G3D_OK;
+}
+
+int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
+                        const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
+                        int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
+                        void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
+    if (rc != G3D_OK) return rc;
+    if (n_mesh == 0) return G3D_OK;
+    TdfWs w = carve(ws, n_mesh, total_tris, p);
+    if (w.bytes > ws_bytes || (!ws && w.bytes)) {
+        set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+        return G3D_ERR_WORKSPACE;
+    }
+    const int sms = sm_count();
+    const int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32;
+    const float far = (float)(p.ni + p.nj + p.nk) * p.dx;                  // cpp:123
+    union { float f; uint32_t u; } fb; fb.f = far;
+    const u64 init = ((u64)fb.u << 32) | 0xffffffffull;                      // closest_tri = -1
+
+    tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
+        w.key, n_mesh * nvox, init, w.parity, n_mesh * pw, out.status, n_mesh,
+        (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
+    if (total_tris > 0) {
+        tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
+            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status);
+        tdf_init_kernel<<<grid_for(total_tris * 32, 256, sms * 32), 256, 0, stream>>>(
+            w.tri, w.box, tri_off, total_tris, p, w.key, far);
+        const int nlev = nlev_of(p);
+        if (nlev > 0) {
+            size_t smem = (size_t)(nlev + 1) * 4;
+            tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start);
+            tdf_sweep_kernel<512><<<n_mesh, 512, smem, stream>>>(w.key, w.tri, tri_off, w.order, w.level_start, nlev, p);
+        }
+    }
+    tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
+        w.key, w.parity, vert_off, tri_off, n_mesh, p, out, 1);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+int tdf_from_sdf_launch(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog, cudaStream_t stream)
+{
+    if (n < 0 || (!sdf && n)) { set_error("bad sdf/n"); return G3D_ERR_INVALID; }
+    if (n == 0) return G3D_OK;
+    tdf_from_sdf_kernel<<<grid_for(n, 256, sm_count() * 16), 256, 0, stream>>>(sdf, n, trunc, tdf, tdflog);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+int unpack_occ_launch(const uint32_t* bits, int64_t n_bits, float* outp, cudaStream_t stream)
+{
+    if (n_bits < 0 || ((!bits || !outp) && n_bits)) { set_error("bad bits/out"); return G3D_ERR_INVALID; }
+    if (n_bits == 0) return G3D_OK;
+    unpack_occ_kernel<<<grid_for(n_bits, 256, sm_count() * 16), 256, 0, stream>>>(bits, n_bits, outp);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+}  // namespace g3d

@@ -102,6 +102,10 @@ def pose_json_payload(k, deg_per_view=15.0):
     return [float(x) for x in pose.T.reshape(-1)]
 
 
+def _cross2(a, b):
+    return a[0] * b[1] - a[1] * b[0]
+
+
 def _hull_mask(pts, H, W):
     """Boolean H x W mask of pixel centres inside the convex hull of 2-D pts."""
     pts = np.unique(np.round(pts, 6), axis=0)
@@ -113,7 +117,7 @@ def _hull_mask(pts, H, W):
     def half(seq):
         out = []
         for p in seq:
-            while len(out) >= 2 and np.cross(out[-1] - out[-2], p - out[-2]) <= 0:
+            while len(out) >= 2 and _cross2(out[-1] - out[-2], p - out[-2]) <= 0:
                 out.pop()
             out.append(p)
         return out

@@ -1,0 +1,201 @@
+"""GPU parity tests of the distance-field path: CUDA (through the C ABI) vs the CPU oracle,
+the compiled reference and the golden fixtures. Bit-exact for faithful mode."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from generate3d_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _oracle_full(oracle, v, t, dim):
+    g = oracle.dfgen_geometry(dim)
+    r = oracle.make_level_set3(t, v, g["origin"], g["dx"], dim, dim, dim)
+    r["sdf"] = r["phi"] * np.float32(dim)
+    return r
+
+
+def _run(dfgen, meshes, dim=32, mode="faithful", outputs=("sdf", "tdf", "tdflog", "occ_bits", "occ_f32", "closest_tri", "status")):
+    voff, toff = [0], [0]
+    for v, t in meshes:
+        voff.append(voff[-1] + len(v))
+        toff.append(toff[-1] + len(t))
+    V = np.concatenate([m[0].reshape(-1, 3) for m in meshes], 0).astype(np.float32)
+    T = np.concatenate([m[1].reshape(-1, 3) for m in meshes], 0).astype(np.uint32)
+    r = dfgen.tdf_batch(V, np.asarray(voff, np.int64), T, np.asarray(toff, np.int64), dim=dim, mode=mode, outputs=outputs)
+    torch.cuda.synchronize()
+    return {k: x.cpu().numpy() for k, x in r.items()}
+
+
+@pytest.mark.parametrize("n,dim,seed", [(9, 32, 0), (9, 32, 1), (18, 32, 2), (5, 64, 3), (3, 16, 4)])
+def test_faithful_bit_exact_vs_oracle(g3d, oracle, n, dim, seed):
+    from generate3d_b200 import dfgen
+    v, t = S.table_mesh(n, seed)
+    want = _oracle_full(oracle, v, t, dim)
+    got = _run(dfgen, [(v, t)], dim)
+    assert got["status"][0] == 0
+    assert np.array_equal(_bits(got["sdf"][0]), _bits(want["sdf"]))
+    assert np.array_equal(got["closest_tri"][0], want["closest_tri"])
+    occ = oracle.occupancy(want["sdf"])
+    assert np.array_equal(got["occ_f32"][0].astype(np.uint8), occ)
+    bits = np.unpackbits(got["occ_bits"][0].view(np.uint8), bitorder="little")[:dim ** 3].reshape(dim, dim, dim)
+    assert np.array_equal(bits, occ)
+    tdf = oracle.load_df_clamp(want["sdf"], 3.0)
+    assert np.array_equal(_bits(got["tdf"][0]), _bits(tdf))
+    assert np.abs(got["tdflog"][0] - oracle.apply_log_transform(tdf)).max() <= 1e-5      # north-star tolerance
+    if oracle.ref_available():
+        g = oracle.dfgen_geometry(dim)
+        ref = oracle.ref_make_level_set3(t, v, g["origin"], g["dx"], dim, dim, dim) * np.float32(dim)
+        assert np.array_equal(_bits(got["sdf"][0]), _bits(ref))
+
+
+def test_faithful_ragged_batch_with_bad_and_empty_meshes(g3d, oracle):
+    from generate3d_b200 import dfgen
+    rng = np.random.default_rng(3)
+    meshes = [S.table_mesh(4, 10), S.table_mesh(7, 11, scale=0.8, rot_y=0.7), S.table_mesh(2, 12)]
+    # degenerate triangles: repeated vertices, collinear, zero area, far outside the cube
+    v, t = S.table_mesh(3, 13)
+    t = t.copy()
+    t[5] = [t[5][0], t[5][0], t[5][1]]
+    t[9] = [t[9][2], t[9][2], t[9][2]]
+    v = np.concatenate([v, np.float32([[3, 3, 3], [3.1, 3, 3], [3, 3.2, 3], [0, 0, 0], [0.1, 0.1, 0.1], [0.2, 0.2, 0.2]])], 0)
+    nv = len(v)
+    t = np.concatenate([t, np.uint32([[nv - 6, nv - 5, nv - 4], [nv - 3, nv - 2, nv - 1]])], 0)
+    meshes.append((v, t))
+    empty = (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    meshes.append(empty)
+    bv, bt = S.table_mesh(2, 14)
+    bt = bt.copy()
+    bt[3, 1] = len(bv) + 7                                  # out-of-range index
+    meshes.append((bv, bt))
+    meshes.append(S.table_mesh(5, 15))                      # a good mesh after the bad ones
+    got = _run(dfgen, meshes, 32)
+    assert got["status"].tolist() == [0, 0, 0, 0, 2, 1, 0]
+    for m in (0, 1, 2, 3, 6):
+        want = _oracle_full(oracle, meshes[m][0], meshes[m][1], 32)
+        assert np.array_equal(_bits(got["sdf"][m]), _bits(want["sdf"])), m
+        assert np.array_equal(got["closest_tri"][m], want["closest_tri"]), m
+    # empty mesh: the reference's initial field (ni+nj+nk)*dx scaled, no triangle anywhere
+    assert np.all(got["sdf"][4] == np.float32(96 * 0.03125 * 32)) and np.all(got["closest_tri"][4] == -1)
+    # mesh with one bad face = the same mesh without that face
+    want = _oracle_full(oracle, bv, np.delete(bt, 3, 0), 32)
+    assert np.array_equal(_bits(got["sdf"][5]), _bits(want["sdf"]))
+
+
+def test_faithful_random_soup_and_noncubic_grid(g3d, oracle):
+    from generate3d_b200 import dfgen, _lib
+    rng = np.random.default_rng(5)
+    v = rng.uniform(-0.6, 0.6, (300, 3)).astype(np.float32)     # pokes outside the cube
+    t = rng.integers(0, 300, (500, 3)).astype(np.uint32)
+    origin = np.float32([-0.55, -0.5, -0.45])
+    ni, nj, nk = 37, 25, 19                                     # not multiples of 32: atomicOr occupancy path
+    want = oracle.make_level_set3(t, v, origin, 0.04, ni, nj, nk)
+    phi, ct = dfgen.make_level_set3(t, v, origin, 0.04, ni, nj, nk, return_closest_tri=True)
+    assert np.array_equal(_bits(phi.cpu().numpy()), _bits(want["phi"]))
+    assert np.array_equal(ct.cpu().numpy(), want["closest_tri"])
+    p = _lib.TdfParams()
+    p.ni, p.nj, p.nk = ni, nj, nk
+    p.origin[:] = [float(x) for x in origin]
+    p.dx, p.out_scale, p.trunc, p.occ_thresh, p.mode, p.exact_band = 0.04, 25.0, 3.0, 1.0, 0, 1
+    r = dfgen.tdf_batch_params(v, np.array([0, 300]), t, np.array([0, 500]), p, ("sdf", "occ_bits", "occ_f32"))
+    occ = oracle.occupancy(want["phi"] * np.float32(25.0))
+    assert np.array_equal(r["occ_f32"][0].cpu().numpy().astype(np.uint8), occ)
+    bits = np.unpackbits(r["occ_bits"][0].cpu().numpy().view(np.uint8), bitorder="little")[:ni * nj * nk]
+    assert np.array_equal(bits.reshape(nk, nj, ni), occ)
+
+
+def test_stages_init_and_parity(g3d, oracle):
+    """Unit-level parity: band init (phi, closest_tri) and intersection parity, via exact_band/sign."""
+    from generate3d_b200 import dfgen
+    v, t = S.table_mesh(6, 21)
+    g = oracle.dfgen_geometry(32)
+    full = oracle.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32)
+    phi = dfgen.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32).cpu().numpy()
+    # sign pattern == running parity of the oracle's intersection counts (makelevelset3.cpp:174-182)
+    par = (np.cumsum(full["isect"], axis=2) % 2) == 1
+    assert np.array_equal(np.signbit(phi), par)
+    # exact_band = 2 changes the init boxes; still bit-equal
+    want2 = oracle.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32, exact_band=2)
+    phi2 = dfgen.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32, exact_band=2).cpu().numpy()
+    assert np.array_equal(_bits(phi2), _bits(want2["phi"]))
+
+
+def test_golden_df_bytes_and_loader_dropins(g3d, golden_dir, tmp_path):
+    from generate3d_b200 import dataset_loader, dfgen, losses
+    z = np.load(os.path.join(golden_dir, "loader.npz"))
+    obj = tmp_path / "model_normalized.obj"
+    with open(obj, "w") as f:
+        for p in z["verts"]:
+            f.write("v %.9g %.9g %.9g\n" % tuple(p))
+        for tri in z["tris"]:
+            f.write("f %d %d %d\n" % tuple(tri + 1))
+    out = tmp_path / "m__0__.df"
+    dfgen.dfgen(str(obj), 32, 0, 1, str(out), write_occ_txt=True)
+    assert out.read_bytes() == bytes(z["df_file"])                       # byte-identical to the reference pipeline
+    df3 = dataset_loader.load_df(str(out), 3.0)
+    assert df3.is_cuda and tuple(df3.shape) == (1, 32, 32, 32)
+    assert np.array_equal(df3.cpu().numpy(), z["tdf3"])
+    occ = dataset_loader.load_occ(str(tmp_path / "m__0__.txt"))
+    assert np.array_equal(occ.cpu().numpy().astype(np.uint8), z["occ_gt"])
+    tl = losses.apply_log_transform(df3)
+    assert np.abs(tl.cpu().numpy() - z["tdflog3"]).max() <= 1e-5
+    # the C++ CLI writes the same bytes
+    cli = os.path.join(os.path.dirname(g3d.LIB_PATH), "bin", "dfgen")
+    out2 = tmp_path / "cli.df"
+    subprocess.check_call([cli, str(obj), "32", "0", "1", str(out2)], stdout=subprocess.DEVNULL)
+    assert out2.read_bytes() == bytes(z["df_file"])
+    assert subprocess.call([cli, str(obj), "32"], stdout=subprocess.DEVNULL) == 255      # usage, exit(-1)
+
+
+def test_host_buffer_abi_matches_device_abi(g3d, oracle):
+    v, t = S.table_mesh(5, 31)
+    L = g3d.lib()
+    ctx = C.c_void_p()
+    g3d.check(L.g3d_context_create(0, C.byref(ctx)))
+    p = g3d.TdfParams()
+    g2w = np.zeros(16, np.float32)
+    g3d.check(L.g3d_dfgen_geometry(32, 0, 1, None, None, C.byref(p), g2w.ctypes.data))
+    p.trunc, p.occ_thresh, p.mode = 3.0, 1.0, 0
+    sdf = np.empty((2, 32, 32, 32), np.float32)
+    bits = np.empty((2, 1024), np.uint32)
+    status = np.empty(2, np.int32)
+    o = g3d.TdfOutputs()
+    o.sdf, o.occ_bits, o.status = sdf.ctypes.data, bits.ctypes.data, status.ctypes.data
+    V = np.concatenate([v, v * np.float32(0.5)], 0)
+    T = np.concatenate([t, t], 0)
+    voff = np.array([0, len(v), 2 * len(v)], np.int64)
+    toff = np.array([0, len(t), 2 * len(t)], np.int64)
+    g3d.check(L.g3d_tdf_batch_host(ctx, V.ctypes.data, voff.ctypes.data, T.ctypes.data, toff.ctypes.data, 2,
+                                   C.byref(p), C.byref(o)))
+    L.g3d_context_destroy(ctx)
+    assert status.tolist() == [0, 0]
+    for m, vv in enumerate((v, v * np.float32(0.5))):
+        want = _oracle_full(oracle, vv, t, 32)
+        assert np.array_equal(_bits(sdf[m]), _bits(want["sdf"]))
+        occ = np.unpackbits(bits[m].view(np.uint8), bitorder="little").reshape(32, 32, 32)
+        assert np.array_equal(occ, oracle.occupancy(want["sdf"]))
+
+
+def test_full_size_batch_properties(g3d, oracle):
+    """BASELINE config 3 shape (n=18, 19,440 triangles) at a reduced count: every mesh of the batch equals the
+    single-mesh result (batch independence), spot-checked against the oracle."""
+    from generate3d_b200 import dfgen
+    V, voff, T, toff = S.table_batch(24, 18, first_seed=100)
+    r = dfgen.tdf_batch(V, voff, T, toff, outputs=("sdf", "status"))
+    sdf = r["sdf"].cpu().numpy()
+    assert not r["status"].any()
+    for m in (0, 7, 23):
+        v, t = V[voff[m]:voff[m + 1]], T[toff[m]:toff[m + 1]]
+        one = dfgen.tdf_batch(v, np.array([0, len(v)]), t, np.array([0, len(t)]), outputs=("sdf",))["sdf"][0].cpu().numpy()
+        assert np.array_equal(_bits(one), _bits(sdf[m]))
+    want = _oracle_full(oracle, V[voff[7]:voff[8]], T[toff[7]:toff[8]], 32)
+    assert np.array_equal(_bits(sdf[7]), _bits(want["sdf"]))
