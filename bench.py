@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- TDF voxels/s and raycast rays/s of the generate3D voxel data-generation hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  * TDF: BASELINE.json configs[2] -- 1,024 table meshes (19,440 triangles each) -> 32^3 sdf + tdf
+    (trunc 3) + tdflog + bit-packed |sdf|<=1 occupancy, reference-faithful mode (bit-exact);
+  * raycast: configs[1] -- 20 depth views 256x256 of one model -> 20 occupancy grids, plus a batched
+    variant (many models x 20 views, larger than L2) for the HBM roofline.
+The headline metric/value of the JSON line is the TDF one; the raycast figures ride along under "raycast".
+Inputs are resident in HBM when the timed region starts ("value"); "e2e" repeats the measurement through
+the host-buffer C ABI (g3d_tdf_batch_host) with pinned host arrays, H2D and D2H copies inside the timed
+region. Multi-GPU: every rank runs the same per-GPU batch on its own models (weak scaling, no
+collective on the data path); time = max over ranks.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref: makelevelset3.cpp compiled in
+place; else the C port in oracle/) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_EVAL = 76            # one point-triangle evaluation, inside-triangle path
+DIM, TRUNC = 32, 3.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--meshes", type=int, default=1024, help="meshes per GPU per step (configs[2]: 1024)")
+    ap.add_argument("--n", type=int, default=18, help="quad-grid resolution of the table: T = 60 n^2")
+    ap.add_argument("--mode", default="faithful", choices=["faithful", "exact"])
+    ap.add_argument("--ray-models", type=int, default=512, help="models x 20 views in the batched raycast leg")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="meshes in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while a timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU arms
+
+def cpu_tdf_reference(V, voff, T, toff, meshes, threads):
+    """Time the reference make_level_set3 (or the C port) on `meshes` models with `threads` host threads.
+    Returns (seconds, kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    g = O.dfgen_geometry(DIM)
+    use_ref = O.ref_available(ndebug=False)
+    kind = "reference" if use_ref else "port"
+
+    def one(m):
+        v, t = V[voff[m]:voff[m + 1]], T[toff[m]:toff[m + 1]]
+        if use_ref:
+            phi = O.ref_make_level_set3(t, v, g["origin"], g["dx"], DIM, DIM, DIM)       # as shipped: asserts on
+        else:
+            phi = O.make_level_set3(t, v, g["origin"], g["dx"], DIM, DIM, DIM)["phi"]
+        return float(phi[0, 0, 0])
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for m in meshes:
+            one(m)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, meshes))
+    return time.perf_counter() - t0, kind
+
+
+def cpu_raycast_port(depth, poses, focal):
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    for q in range(depth.shape[0]):
+        O.raycast_depth(depth[q], poses[q], DIM, focal)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from generate3d_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    per_step = max(4, min(args.meshes, 2 * cores))
+    V, voff, T, toff = S.table_batch(per_step, args.n, first_seed=0)
+    times = []
+    kind = "port"
+    for it in range(args.warmup + args.steps):
+        dt, kind = cpu_tdf_reference(V, voff, T, toff, list(range(per_step)), cores)
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = per_step * DIM ** 3 / (ms * 1e-3)
+    d, p = S.depth_views(4, 256, 256)
+    ray_s = cpu_raycast_port(d, p, 262.5)
+    sample = "%d of %d meshes per step (n=%d, %d tris), %d threads" % (per_step, args.meshes, args.n, 60 * args.n ** 2, cores)
+    line = {
+        "impl": "reference", "metric": "tdf_voxels_per_s", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: batch of synthetic ~20k-tri table meshes -> 32^3 TDF + occupancy "
+                               "(reference CPU make_level_set3, bounded sample)", "meshes_per_step": per_step,
+                   "tris_per_mesh": 60 * args.n ** 2, "dim": DIM, "trunc": TRUNC},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "raycast": {"metric": "raycast_rays_per_s", "value": 4 * 256 * 256 / ray_s, "unit": "rays/s", "kind": "port",
+                    "sample": "4 views 256x256, numpy restatement of raycast_depth, 1 thread"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+
+def run_b200(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from generate3d_b200 import _lib, dfgen, raytracing, shard, synthetic as S
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    peaks, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic workload (per rank: its own models, seeds offset by rank)
+    M = args.meshes
+    V, voff, T, toff = S.table_batch(M, args.n, first_seed=rank * M)
+    dV = torch.from_numpy(V).to(dev)
+    dT = torch.from_numpy(T.view(np.int32)).to(dev)
+    dvoff, dtoff = torch.from_numpy(voff).to(dev), torch.from_numpy(toff).to(dev)
+    outputs = ("sdf", "tdf", "tdflog", "occ_bits", "status")
+    input_mb = (V.nbytes + T.nbytes) / 1e6
+
+    def tdf_step(out):
+        return dfgen.tdf_batch(dV, dvoff, dT, dtoff, dim=DIM, trunc=TRUNC, mode=args.mode, outputs=outputs, out=out)
+
+    # instrumented (untimed) run: how many point-triangle evaluations one step performs
+    _lib.check(L.g3d_profile_enable(2))
+    out = tdf_step(None)
+    torch.cuda.synchronize()
+    ev = (C.c_uint64 * 4)()
+    _lib.check(L.g3d_profile_read(None, ev))
+    evals = {"init": int(ev[0]), "sweep": int(ev[1]), "exact_pairs": int(ev[2]), "exact_box_tests": int(ev[3])}
+    assert int(out["status"].sum().item()) == 0
+    _lib.check(L.g3d_profile_enable(1))            # per-kernel events only, from here on
+
+    for _ in range(args.warmup):
+        tdf_step(out)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = np.zeros(8)
+    sm = (C.c_float * 8)()
+    e0.record()
+    for _ in range(args.steps):
+        tdf_step(out)
+        _lib.check(L.g3d_profile_read(sm, None))   # waits for this step's last kernel (steps are >10 ms)
+        stage += np.frombuffer(sm, np.float32)
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    ms_step = shard.all_reduce_max(e0.elapsed_time(e1) / args.steps, dev)
+    stage /= args.steps
+    total_vox = shard.all_reduce_sum(M * DIM ** 3, dev)
+    value = total_vox / (ms_step * 1e-3)
+    tdf_launches = 6 * args.steps if args.mode == "faithful" else 4 * args.steps
+
+    names = ["fill", "prep", "band_init", "order", "sweep", "finalize", "exact", "raycast"]
+    stages_ms = {n: round(float(s), 4) for n, s in zip(names, stage) if s > 0}
+    dom = "sweep" if args.mode == "faithful" else "exact"
+    dom_ms = stages_ms.get(dom, 0.0)
+    dom_evals = evals["sweep"] if args.mode == "faithful" else evals["exact_pairs"]
+    tf = C.c_float()
+    _lib.check(L.g3d_probe_fp32_tflops(C.byref(tf), None))
+    props = torch.cuda.get_device_properties(dev)
+    nominal = props.multi_processor_count * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    achieved = FLOP_PER_EVAL * dom_evals / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
+    roofline = {
+        "kernel": "tdf_sweep_kernel" if args.mode == "faithful" else "tdf_exact_kernel", "bound": "fp32",
+        "achieved": achieved, "peak": float(tf.value), "unit": "TFLOP/s", "frac": achieved / float(tf.value) if tf.value else None,
+        "peak_source": "on-box FFMA probe (g3d_probe_fp32_tflops); MEASURED_PEAKS.json has no FP32 figure",
+        "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
+        "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": dom_evals, "kernel_ms": dom_ms,
+        "note": "faithful arithmetic issues no FMA (bit parity with the CPU reference), so 0.5 of the FMA peak is its ceiling",
+        "traffic": None,
+    }
+
+    # ---- raycast: configs[1] (20 views 256^2, one launch) and a batched leg (> L2) for the HBM roofline
+    d20, p20 = S.depth_views(20, 256, 256)
+    dd20, dp20 = torch.from_numpy(d20).to(dev), torch.from_numpy(p20).to(dev)
+
+    def time_raycast(dd, dp, steps, warm):
+        for _ in range(warm):
+            raytracing.raycast_batch(dd, dp, focal=262.5, outputs=("occ_bits",))
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            raytracing.raycast_batch(dd, dp, focal=262.5, outputs=("occ_bits",))
+        b.record()
+        barrier()
+        return a.elapsed_time(b) / steps
+
+    ms20 = shard.all_reduce_max(time_raycast(dd20, dp20, max(args.steps, 20), max(args.warmup, 3)), dev)
+    RM = args.ray_models
+    ddb = dd20.repeat(RM, 1, 1)                              # RM models x 20 views (same pixels, distinct buffers)
+    dpb = dp20.repeat(RM, 1, 1)
+    msb = shard.all_reduce_max(time_raycast(ddb, dpb, args.steps, args.warmup), dev)
+    nview_b = 20 * RM
+    bytes_per_view = 256 * 256 + 64 + DIM ** 3 // 8
+    ray_bw = nview_b * bytes_per_view / (msb * 1e-3) / 1e9
+    raycast = {
+        "metric": "raycast_rays_per_s", "unit": "rays/s",
+        "config1": {"workload": "configs[1]: 20 depth views 256x256 of one model -> 20 x 32^3 occupancy, one launch",
+                    "value": world * 20 * 256 * 256 / (ms20 * 1e-3), "ms_per_step": ms20},
+        "batched": {"workload": "%d models x 20 views 256x256 per GPU (%.0f MB depth > 126 MB L2)" % (RM, nview_b * 65536 / 1e6),
+                    "value": world * nview_b * 256 * 256 / (msb * 1e-3), "ms_per_step": msb},
+        "roofline": {"kernel": "raycast_kernel", "bound": "hbm", "achieved": ray_bw, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": ray_bw / peaks["hbm_gbs"], "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs",
+                     "bytes_per_view": bytes_per_view, "traffic": None},
+    }
+    ray_launches = max(args.steps, 20) + args.steps
+
+    # ---- e2e through the host-buffer C ABI: pinned host arrays in, sdf + occupancy bits + status out
+    e2e = None
+    if not args.no_e2e:
+        ctx = C.c_void_p()
+        _lib.check(L.g3d_context_create(local, C.byref(ctx)))
+        hV, hT = torch.from_numpy(V).pin_memory(), torch.from_numpy(T.view(np.int32)).pin_memory()
+        hsdf = torch.empty((M, DIM, DIM, DIM), dtype=torch.float32).pin_memory()
+        hbits = torch.empty((M, DIM ** 3 // 32), dtype=torch.int32).pin_memory()
+        hstat = torch.empty((M,), dtype=torch.int32).pin_memory()
+        p, _ = dfgen.dfgen_geometry(DIM, 0, 1)
+        p.trunc, p.occ_thresh, p.mode = TRUNC, 1.0, 0 if args.mode == "faithful" else 1
+        o = _lib.TdfOutputs()
+        o.sdf, o.occ_bits, o.status = hsdf.data_ptr(), hbits.data_ptr(), hstat.data_ptr()
+
+        def e2e_step():
+            _lib.check(L.g3d_tdf_batch_host(ctx, hV.data_ptr(), voff.ctypes.data, hT.data_ptr(), toff.ctypes.data, M,
+                                            C.byref(p), C.byref(o)))
+        _lib.check(L.g3d_profile_enable(0))
+        for _ in range(max(1, args.warmup)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()                                       # returns after its D2H copies have completed
+        dt = (time.perf_counter() - t0) / args.steps
+        barrier()
+        dt = shard.all_reduce_max(dt, dev)
+        assert int(hstat.sum()) == 0
+        e2e = {"value": total_vox / dt, "unit": "voxels/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(V.nbytes + T.nbytes + voff.nbytes + toff.nbytes),
+               "d2h_bytes_per_step": int(hsdf.numel() * 4 + hbits.numel() * 4 + hstat.numel() * 4),
+               "api": "g3d_tdf_batch_host (pinned host buffers; outputs: sdf + occupancy bits + status)"}
+        L.g3d_context_destroy(ctx)
+        tdf_launches += 6 * args.steps if args.mode == "faithful" else 4 * args.steps
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's make_level_set3, one thread
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = args.cpu_sample or 40
+        ns = min(ns, M)
+        secs, kind = cpu_tdf_reference(V, voff, T, toff, list(range(ns)), 1)
+        cpu = {"value": ns * DIM ** 3 / secs, "unit": "voxels/s", "cores": 1, "kind": kind,
+               "sample": "first %d of the %d meshes of the step, single thread (the reference is single-threaded), %.1f s" % (ns, M, secs)}
+        rs = cpu_raycast_port(d20[:4], p20[:4], 262.5)
+        raycast["cpu_baseline"] = {"value": 4 * 65536 / rs, "unit": "rays/s", "cores": 1, "kind": "port",
+                                   "sample": "4 of the 20 views, numpy restatement of raycast_depth (the reference's Python loop "
+                                             "takes ~1.8 s/view, BASELINE.md)"}
+
+    if rank == 0:
+        line = {
+            "metric": "tdf_voxels_per_s", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: batch of 1,024 synthetic ~20k-tri table meshes -> 32^3 TDF (trunc 3) + tdflog + "
+                                   "occupancy per B200", "meshes_per_gpu": M, "tris_per_mesh": 60 * args.n ** 2, "dim": DIM,
+                       "trunc": TRUNC, "mode": args.mode, "outputs": list(outputs),
+                       "l2": "inputs %.0f MB + outputs %.0f MB per step, larger than the 126 MB L2 (no explicit flush)" % (input_mb, M * DIM ** 3 * 12.125 / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": tdf_launches + ray_launches, "roofline": roofline,
+            "cpu_baseline": cpu, "stages_ms": stages_ms, "evals_per_step": evals, "raycast": raycast,
+            "pair_rate_nominal_per_s": world * M * DIM ** 3 * 60 * args.n ** 2 / (ms_step * 1e-3),
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        from generate3d_b200 import shard
+        shard.init_process_group("nccl")
+    try:
+        run_b200(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

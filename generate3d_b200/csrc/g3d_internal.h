@@ -44,4 +44,10 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
 
 int sm_count();
 
+// ---- profiling hooks (g3d_capi.cu); no-ops unless g3d_profile_enable was called on this thread
+enum { ST_FILL = 0, ST_PREP, ST_INIT, ST_ORDER, ST_SWEEP, ST_FINAL, ST_EXACT, ST_RAYCAST, ST_COUNT };
+void prof_begin(cudaStream_t s);                    // start of an API call: resets marks + counters
+void prof_mark(int stage, cudaStream_t s);          // call right AFTER launching the kernel(s) of `stage`
+unsigned long long* prof_counters();                // device u64[4] or nullptr
+
 }  // namespace g3d

@@ -193,9 +193,11 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     if (occ_bits && ((dim * dim) & 31))
         G3D_CUDA_TRY(cudaMemsetAsync(occ_bits, 0, (size_t)n_view * ((nvox + 31) / 32) * 4, stream));
     dim3 grid((unsigned)n_view, (unsigned)((dim + zs - 1) / zs));
+    prof_begin(stream);
     raycast_kernel<NT><<<grid, NT, smem, stream>>>(depth, pose, H, W, focal, cx, cy, clamp_max, dim, zs,
                                                    1.0f / (float)dim, occ_bits, occ_f32,
                                                    reinterpret_cast<long long*>(index_map));
+    prof_mark(ST_RAYCAST, stream);
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
 }

@@ -214,8 +214,9 @@ __device__ __forceinline__ V3 node_pos(int i, int j, int k, const g3d_tdf_params
 __global__ void __launch_bounds__(256)
 tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
                 const int64_t* __restrict__ tri_off, int64_t total_tris, g3d_tdf_params P,
-                u64* __restrict__ key, float far)
+                u64* __restrict__ key, float far, u64* counter)
 {
+    u64 n_eval = 0;
     const int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -234,6 +235,7 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
             int i = i0 + q % bi, r = q / bi;
             int j = j0 + r % bj, k = k0 + r / bj;
             float d = point_triangle_distance(node_pos(i, j, k, P), x1, x2, x3);
+            ++n_eval;
             u64* kp = K + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k));
             float cur = __uint_as_float((uint32_t)(*(volatile u64*)kp >> 32));
             // d < far mirrors the very first `d < phi`; d <= cur lets an equal
@@ -241,6 +243,7 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
             if (d < far && d <= cur) atomicMin(kp, ((u64)__float_as_uint(d) << 32) | tl);
         }
     }
+    if (counter && n_eval) atomicAdd(counter, n_eval);
 }
 
 // ----------------------------------------------------------- sweep order ----
@@ -276,8 +279,9 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                  const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
-                 g3d_tdf_params P)
+                 g3d_tdf_params P, u64* counter)
 {
+    u64 n_eval = 0;
     extern __shared__ int32_t s_lev[];             // [nlev + 1]
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
     __syncthreads();
@@ -334,6 +338,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                             float4 a1 = __ldg(T + 3 * t), a2 = __ldg(T + 3 * t + 1), a3 = __ldg(T + 3 * t + 2);
                             float d = point_triangle_distance(gx, { a1.x, a1.y, a1.z }, { a2.x, a2.y, a2.z },
                                                               { a3.x, a3.y, a3.z });
+                            ++n_eval;
                             if (d < phi) { phi = d; ct = t; changed = true; }
                         }
                         need >>= 1;
@@ -345,6 +350,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
             __syncthreads();
         }
     }
+    if (counter && n_eval) atomicAdd(counter + 1, n_eval);
 }
 
 // -------------------------------------------------------------- finalize ----
@@ -477,23 +483,31 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
     union { float f; uint32_t u; } fb; fb.f = far;
     const u64 init = ((u64)fb.u << 32) | 0xffffffffull;                      // closest_tri = -1
 
+    prof_begin(stream);
+    u64* cnt = prof_counters();
     tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
         w.key, n_mesh * nvox, init, w.parity, n_mesh * pw, out.status, n_mesh,
         (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
+    prof_mark(ST_FILL, stream);
     if (total_tris > 0) {
         tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
             verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status);
+        prof_mark(ST_PREP, stream);
         tdf_init_kernel<<<grid_for(total_tris * 32, 256, sms * 32), 256, 0, stream>>>(
-            w.tri, w.box, tri_off, total_tris, p, w.key, far);
+            w.tri, w.box, tri_off, total_tris, p, w.key, far, cnt);
+        prof_mark(ST_INIT, stream);
         const int nlev = nlev_of(p);
         if (nlev > 0) {
             size_t smem = (size_t)(nlev + 1) * 4;
             tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start);
-            tdf_sweep_kernel<512><<<n_mesh, 512, smem, stream>>>(w.key, w.tri, tri_off, w.order, w.level_start, nlev, p);
+            prof_mark(ST_ORDER, stream);
+            tdf_sweep_kernel<512><<<n_mesh, 512, smem, stream>>>(w.key, w.tri, tri_off, w.order, w.level_start, nlev, p, cnt);
+            prof_mark(ST_SWEEP, stream);
         }
     }
     tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
         w.key, w.parity, vert_off, tri_off, n_mesh, p, out, 1);
+    prof_mark(ST_FINAL, stream);
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
 }

@@ -170,6 +170,22 @@ int g3d_write_df(const char* path, const int32_t* dims3, float res, const float*
 int g3d_read_df(const char* path, int32_t* dims3, float* res, float* grid2world16, float* sdf,
                 int64_t capacity);
 
+/* ------------------------------------------------------------ profiling ----
+ * Off by default. flags bit 0: record a CUDA event on the caller's stream between the kernels
+ * of each g3d_tdf_batch / g3d_raycast_batch call (bench.py's per-kernel timing);
+ * bit 1: count point-triangle evaluations with device atomics (the "instrumented run" the
+ * algorithmic-FLOP figure comes from; slows the kernels, never on in a timed region).
+ * g3d_profile_read waits for the last call's events. stage_ms[8]: 0 fill, 1 prep, 2 band init,
+ * 3 sweep-order table, 4 sweeps, 5 finalize, 6 exact-mode main kernel, 7 raycast (0 if not run).
+ * evals[4]: band-init evaluations, sweep evaluations, exact-mode evaluated pairs, exact-mode
+ * culled-box tests. State is per host thread. */
+#define G3D_PROF_EVENTS 1
+#define G3D_PROF_COUNT  2
+int g3d_profile_enable(int32_t flags);
+int g3d_profile_read(float* stage_ms8, uint64_t* evals4);
+/* Dependent-FFMA microbenchmark on the current device: achieved FP32 TFLOP/s (FMA = 2 flop). */
+int g3d_probe_fp32_tflops(float* tflops, void* cuda_stream);
+
 /* Mesh reader standing in for load_mesh (src/utils/LoaderMesh.h:15-84): .obj / .ply ->
  * verts f32 [n_vert,3] (ALL vertex records, referenced or not) and tris u32 [n_tri,3] in file
  * order. Buffers are malloc'ed; release with g3d_free. Unknown extension -> G3D_ERR_INVALID
