@@ -5,7 +5,8 @@
 // order-independent parallel steps:
 //
 //  tdf_prep      one thread / triangle: gathers the three vertices into a
-//                48-byte record, computes the double-precision grid coordinates,
+//                64-byte record (vertices + the per-triangle invariants of the
+//                distance function), computes the double-precision grid coordinates,
 //                the band box [int(min)-b, int(max)+b+1] (cpp:131-137) and the
 //                x-ray intersection counts (cpp:147-160). Only the PARITY of the
 //                counts is ever used (cpp:178), so they are kept as XOR-ed bits.
@@ -26,10 +27,11 @@
 //                (vox2mesh/main.cpp:92), clamp at trunc (dataset_loader.py:
 //                137-139), sign*log(|x|+1) (losses.py:7-11).
 //
-// HBM layout (workspace): tri records [T_total] 48 B; band boxes [T_total] 16 B;
+// HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B;
 // keys u64 [n_mesh, nk, nj, ni] (hi = phi bits, lo = closest_tri); parity bits
 // u32 [n_mesh, ceil(nvox/32)]; sweep order table (shared by all meshes).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "g3d_internal.h"
 #include "g3d_ptd.cuh"
@@ -41,7 +43,7 @@ namespace {
 typedef unsigned long long u64;
 
 struct TdfWs {
-    float4*   tri;          // 3 x float4 per triangle: x1, x2, x3 (w unused)
+    float4*   tri;          // 4 x float4 per triangle: TriRec (g3d_ptd.cuh)
     int4*     box;          // i0|i1<<16, j0|j1<<16, k0|k1<<16, mesh
     u64*      key;
     uint32_t* parity;
@@ -66,7 +68,7 @@ TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params
     int64_t pw = (nvox + 31) / 32;
     int64_t nsweep = (int64_t)(p.ni - 1) * (p.nj - 1) * (p.nk - 1);
     if (nsweep < 0) nsweep = 0;
-    w.tri = (float4*)take((size_t)total_tris * 48);
+    w.tri = (float4*)take((size_t)total_tris * 64);
     w.box = (int4*)take((size_t)total_tris * 16);
     w.key = (u64*)take((size_t)n_mesh * nvox * 8);
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
@@ -152,7 +154,7 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
         // and neutralise the triangle: NaN vertices never win a `<` and an empty box
         if (status) atomicOr(status + m, G3D_MESH_BAD_INDEX);
         float qnan = __int_as_float(0x7fc00000);
-        tri_out[3 * t] = tri_out[3 * t + 1] = tri_out[3 * t + 2] = make_float4(qnan, qnan, qnan, 0.f);
+        tri_out[4 * t] = tri_out[4 * t + 1] = tri_out[4 * t + 2] = tri_out[4 * t + 3] = make_float4(qnan, qnan, qnan, qnan);
         box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
         return;
     }
@@ -160,9 +162,7 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
     const float* pq = verts + 3 * (v0 + iq);
     const float* pr = verts + 3 * (v0 + ir);
     float xp[3] = { pp[0], pp[1], pp[2] }, xq[3] = { pq[0], pq[1], pq[2] }, xr[3] = { pr[0], pr[1], pr[2] };
-    tri_out[3 * t]     = make_float4(xp[0], xp[1], xp[2], 0.f);
-    tri_out[3 * t + 1] = make_float4(xq[0], xq[1], xq[2], 0.f);
-    tri_out[3 * t + 2] = make_float4(xr[0], xr[1], xr[2], 0.f);
+    store_trirec(tri_out + 4 * t, make_trirec({ xp[0], xp[1], xp[2] }, { xq[0], xq[1], xq[2] }, { xr[0], xr[1], xr[2] }));
 
     const int dims[3] = { P.ni, P.nj, P.nk };
     double fp[3], fq[3], fr[3];
@@ -226,15 +226,14 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
         int i0 = b.x & 0xffff, i1 = b.x >> 16, j0 = b.y & 0xffff, j1 = b.y >> 16, k0 = b.z & 0xffff, k1 = b.z >> 16;
         int bi = i1 - i0 + 1, bj = j1 - j0 + 1, bk = k1 - k0 + 1;
         if (bi <= 0 || bj <= 0 || bk <= 0) continue;
-        float4 a1 = __ldg(tri + 3 * t), a2 = __ldg(tri + 3 * t + 1), a3 = __ldg(tri + 3 * t + 2);
-        V3 x1 = { a1.x, a1.y, a1.z }, x2 = { a2.x, a2.y, a2.z }, x3 = { a3.x, a3.y, a3.z };
+        const TriRec rec = load_trirec(tri + 4 * t);
         uint32_t tl = (uint32_t)(t - tri_off[b.w]);
         u64* K = key + (int64_t)b.w * nvox;
         int n = bi * bj * bk;
         for (int q = lane; q < n; q += 32) {
             int i = i0 + q % bi, r = q / bi;
             int j = j0 + r % bj, k = k0 + r / bj;
-            float d = point_triangle_distance(node_pos(i, j, k, P), x1, x2, x3);
+            float d = point_triangle_distance(node_pos(i, j, k, P), rec);
             ++n_eval;
             u64* kp = K + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k));
             float cur = __uint_as_float((uint32_t)(*(volatile u64*)kp >> 32));
@@ -275,21 +274,36 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 }
 
 // ----------------------------------------------------------------- sweep ----
+// One CTA per mesh. Per level each thread owns one node: it reads the closest_tri of
+// its 7 upwind neighbours and decides which of them need a distance evaluation. A
+// candidate equal to the node's own triangle, or to an earlier candidate, re-evaluates
+// to a distance that cannot pass the strict `<` (it equals or exceeds the current
+// phi), so it is skipped -- about 2/3 of the reference's evaluations.
+// The surviving (node, triangle) pairs are unevenly spread over the lanes, so each warp
+// pushes them into a private shared-memory queue, evaluates the queue densely (one pair
+// per lane), and the owners then replay the results in the reference's neighbour order.
+constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
+
 template <int NT>
 __global__ void __launch_bounds__(NT)
 tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                  const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
-                 g3d_tdf_params P, u64* counter)
+                 int lev_words, g3d_tdf_params P, u64* counter)
 {
     u64 n_eval = 0;
-    extern __shared__ int32_t s_lev[];             // [nlev + 1]
+    extern __shared__ uint32_t s_mem[];
+    int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* q_tri = s_mem + lev_words + warp * (3 * kSweepQueue);
+    uint32_t* q_pos = q_tri + kSweepQueue;
+    float* q_res = reinterpret_cast<float*>(q_pos + kSweepQueue);
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
     __syncthreads();
     const int mesh = blockIdx.x;
     const int64_t nvox = nvox_of(P);
     u64* K = key + (int64_t)mesh * nvox;
     const int* Klo = (const int*)K;                // low word of each key = closest_tri
-    const float4* T = tri + 3 * tri_off[mesh];
+    const float4* T = tri + 4 * tri_off[mesh];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int sj = ni, sk = ni * nj;
 
@@ -302,48 +316,74 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
         const int oi = di, oj = dj * sj, ok = dk * sk;
         for (int L = 0; L < nlev; ++L) {
             const int beg = s_lev[L], end = s_lev[L + 1];
-            for (int q = beg + threadIdx.x; q < end; q += NT) {
-                uint32_t o = __ldg(order + q);
-                int a = o & 1023, b = (o >> 10) & 1023, c = o >> 20;
-                int i = di > 0 ? 1 + a : ni - 2 - a;
-                int j = dj > 0 ? 1 + b : nj - 2 - b;
-                int k = dk > 0 ? 1 + c : nk - 2 - c;
-                int n = i + sj * j + sk * k;
-                // the 7 upwind neighbours in the order of cpp:72-78
-                int c0 = Klo[2 * (n - oi)], c1 = Klo[2 * (n - oj)], c2 = Klo[2 * (n - oi - oj)],
-                    c3 = Klo[2 * (n - ok)], c4 = Klo[2 * (n - oi - ok)], c5 = Klo[2 * (n - oj - ok)],
+            for (int qb = beg + warp * 32; qb < end; qb += NT) {
+                const int q = qb + lane;
+                int c0 = -1, c1 = -1, c2 = -1, c3 = -1, c4 = -1, c5 = -1, c6 = -1, ct = -1, n = 0;
+                uint32_t need = 0, pos = 0;
+                float phi = 0.f;
+                if (q < end) {
+                    uint32_t o = __ldg(order + q);
+                    int a = o & 1023, b = (o >> 10) & 1023, c = o >> 20;
+                    int i = di > 0 ? 1 + a : ni - 2 - a;
+                    int j = dj > 0 ? 1 + b : nj - 2 - b;
+                    int k = dk > 0 ? 1 + c : nk - 2 - c;
+                    pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+                    n = i + sj * j + sk * k;
+                    // the 7 upwind neighbours in the order of cpp:72-78
+                    c0 = Klo[2 * (n - oi)]; c1 = Klo[2 * (n - oj)]; c2 = Klo[2 * (n - oi - oj)];
+                    c3 = Klo[2 * (n - ok)]; c4 = Klo[2 * (n - oi - ok)]; c5 = Klo[2 * (n - oj - ok)];
                     c6 = Klo[2 * (n - oi - oj - ok)];
-                u64 kv = K[n];
-                float phi = __uint_as_float((uint32_t)(kv >> 32));
-                int ct = (int)(uint32_t)kv;
-                // A candidate equal to the node's own triangle, or to an earlier
-                // candidate, re-evaluates to a distance that cannot pass the strict
-                // `<` (it equals or exceeds the current phi): skip it.
-                uint32_t need = 0;
-                need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
-                need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
-                need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
-                need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
-                need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
-                need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
-                need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                    u64 kv = K[n];
+                    phi = __uint_as_float((uint32_t)(kv >> 32));
+                    ct = (int)(uint32_t)kv;
+                    need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
+                    need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
+                    need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
+                    need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
+                    need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
+                    need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
+                    need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                }
+                // warp-exclusive prefix of the per-lane work counts
+                const int cnt = __popc(need);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int W = __shfl_sync(0xffffffffu, incl, 31);
+                if (W == 0) continue;
+                const int off = incl - cnt;
+                {
+                    int w = off;
+                    if (need & 1u)  { q_tri[w] = c0; q_pos[w] = pos; ++w; }
+                    if (need & 2u)  { q_tri[w] = c1; q_pos[w] = pos; ++w; }
+                    if (need & 4u)  { q_tri[w] = c2; q_pos[w] = pos; ++w; }
+                    if (need & 8u)  { q_tri[w] = c3; q_pos[w] = pos; ++w; }
+                    if (need & 16u) { q_tri[w] = c4; q_pos[w] = pos; ++w; }
+                    if (need & 32u) { q_tri[w] = c5; q_pos[w] = pos; ++w; }
+                    if (need & 64u) { q_tri[w] = c6; q_pos[w] = pos; ++w; }
+                }
+                __syncwarp();
+                for (int e = lane; e < W; e += 32) {
+                    uint32_t pp = q_pos[e];
+                    V3 gx = node_pos((int)(pp & 1023u), (int)((pp >> 10) & 1023u), (int)(pp >> 20), P);
+                    q_res[e] = point_triangle_distance(gx, load_trirec(T + 4 * (int64_t)q_tri[e]));
+                    ++n_eval;
+                }
+                __syncwarp();
                 if (need) {
-                    V3 gx = node_pos(i, j, k, P);
+                    int r = off;
                     bool changed = false;
-#pragma unroll 1
-                    for (int r = 0; r < 7; ++r) {
-                        int t = c0;
-                        c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = c6;
-                        if (need & 1u) {
-                            float4 a1 = __ldg(T + 3 * t), a2 = __ldg(T + 3 * t + 1), a3 = __ldg(T + 3 * t + 2);
-                            float d = point_triangle_distance(gx, { a1.x, a1.y, a1.z }, { a2.x, a2.y, a2.z },
-                                                              { a3.x, a3.y, a3.z });
-                            ++n_eval;
-                            if (d < phi) { phi = d; ct = t; changed = true; }
-                        }
-                        need >>= 1;
-                        if (!need) break;
-                    }
+                    float d;
+                    if (need & 1u)  { d = q_res[r++]; if (d < phi) { phi = d; ct = c0; changed = true; } }
+                    if (need & 2u)  { d = q_res[r++]; if (d < phi) { phi = d; ct = c1; changed = true; } }
+                    if (need & 4u)  { d = q_res[r++]; if (d < phi) { phi = d; ct = c2; changed = true; } }
+                    if (need & 8u)  { d = q_res[r++]; if (d < phi) { phi = d; ct = c3; changed = true; } }
+                    if (need & 16u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c4; changed = true; } }
+                    if (need & 32u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c5; changed = true; } }
+                    if (need & 64u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c6; changed = true; } }
                     if (changed) K[n] = ((u64)__float_as_uint(phi) << 32) | (uint32_t)ct;
                 }
             }
@@ -446,6 +486,37 @@ int grid_for(int64_t n, int block, int max_blocks)
 
 }  // namespace
 
+namespace {
+template <int NT>
+int launch_sweep_nt(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
+                    cudaStream_t stream)
+{
+    const int lev_words = (nlev + 1 + 3) & ~3;
+    const size_t smem = (size_t)(lev_words + (NT / 32) * 3 * kSweepQueue) * 4;
+    G3D_CUDA_TRY(cudaFuncSetAttribute(tdf_sweep_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tdf_sweep_kernel<NT><<<n_mesh, NT, smem, stream>>>(w.key, w.tri, tri_off, w.order, w.level_start, nlev, lev_words, p, cnt);
+    return G3D_OK;
+}
+
+int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
+                 cudaStream_t stream)
+{
+    // Threads per mesh. Small CTAs win for 32^3-class grids (measured on B200, 1,024 meshes: 128 thr 22.2 ms,
+    // 256 thr 24.4, 512 thr 28.4, 1024 thr 31.1): more meshes are resident per SM, so one mesh's barrier
+    // wait is covered by another mesh's arithmetic. Large grids get more threads per mesh.
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("G3D_SWEEP_THREADS"); forced = e ? atoi(e) : 0; }
+    int64_t widest = (int64_t)(p.ni - 1) * (p.nj - 1);           // upper bound on a level's node count
+    int nt = forced ? forced : (widest >= 16384 ? 1024 : (widest >= 4096 ? 512 : (widest >= 2048 ? 256 : 128)));
+    switch (nt) {
+        case 128: return launch_sweep_nt<128>(n_mesh, nlev, w, tri_off, p, cnt, stream);
+        case 512: return launch_sweep_nt<512>(n_mesh, nlev, w, tri_off, p, cnt, stream);
+        case 1024: return launch_sweep_nt<1024>(n_mesh, nlev, w, tri_off, p, cnt, stream);
+        default: return launch_sweep_nt<256>(n_mesh, nlev, w, tri_off, p, cnt, stream);
+    }
+}
+}  // namespace
+
 size_t tdf_faithful_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
 {
     return carve(nullptr, n_mesh, total_tris, p).bytes;
@@ -501,7 +572,8 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
             size_t smem = (size_t)(nlev + 1) * 4;
             tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start);
             prof_mark(ST_ORDER, stream);
-            tdf_sweep_kernel<512><<<n_mesh, 512, smem, stream>>>(w.key, w.tri, tri_off, w.order, w.level_start, nlev, p, cnt);
+            rc = launch_sweep(n_mesh, nlev, w, tri_off, p, cnt, stream);
+            if (rc != G3D_OK) return rc;
             prof_mark(ST_SWEEP, stream);
         }
     }
