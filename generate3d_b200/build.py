@@ -18,12 +18,11 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 UNITS = {
     "g3d_tdf.cu": ["-fmad=false"],
-    "g3d_tdf_exact.cu": [],
     "g3d_raycast.cu": ["-fmad=false"],
     "g3d_capi.cu": [],
     "g3d_mesh_io.cpp": [],
 }
-HEADERS = ["g3d_internal.h", "g3d_ptd.cuh", os.path.join("..", "..", "include", "g3d.h")]
+HEADERS = ["g3d_internal.h", "g3d_ptd.cuh", "g3d_tdf_exact.cuh", os.path.join("..", "..", "include", "g3d.h")]
 
 
 def _stale(target, sources):

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256)
 tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ vert_off,
                 const uint32_t* __restrict__ tris, const int64_t* __restrict__ tri_off,
                 int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
-                int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status)
+                int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status,
+                float4* __restrict__ aabb_out)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_tris) return;
@@ -156,6 +157,7 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
         float qnan = __int_as_float(0x7fc00000);
         tri_out[4 * t] = tri_out[4 * t + 1] = tri_out[4 * t + 2] = tri_out[4 * t + 3] = make_float4(qnan, qnan, qnan, qnan);
         box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
+        if (aabb_out) aabb_out[2 * t] = aabb_out[2 * t + 1] = make_float4(qnan, qnan, qnan, qnan);
         return;
     }
     const float* pp = verts + 3 * (v0 + ip);
@@ -163,6 +165,19 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
     const float* pr = verts + 3 * (v0 + ir);
     float xp[3] = { pp[0], pp[1], pp[2] }, xq[3] = { pq[0], pq[1], pq[2] }, xr[3] = { pr[0], pr[1], pr[2] };
     store_trirec(tri_out + 4 * t, make_trirec({ xp[0], xp[1], xp[2] }, { xq[0], xq[1], xq[2] }, { xr[0], xr[1], xr[2] }));
+    if (aabb_out) {                                // exact mode: world-space bounding box of the triangle
+        aabb_out[2 * t] = make_float4(fminf(xp[0], fminf(xq[0], xr[0])), fminf(xp[1], fminf(xq[1], xr[1])),
+                                      fminf(xp[2], fminf(xq[2], xr[2])), 0.f);
+        aabb_out[2 * t + 1] = make_float4(fmaxf(xp[0], fmaxf(xq[0], xr[0])), fmaxf(xp[1], fmaxf(xq[1], xr[1])),
+                                          fmaxf(xp[2], fmaxf(xq[2], xr[2])), 0.f);
+        // a non-finite vertex must poison the box (fminf/fmaxf drop NaNs) so the triangle is culled,
+        // exactly as its NaN distances never win in the reference
+        float chk = xp[0] + xp[1] + xp[2] + xq[0] + xq[1] + xq[2] + xr[0] + xr[1] + xr[2];
+        if (!(fabsf(chk) < 3.0e38f)) {
+            float qn = __int_as_float(0x7fc00000);
+            aabb_out[2 * t] = aabb_out[2 * t + 1] = make_float4(qn, qn, qn, qn);
+        }
+    }
 
     const int dims[3] = { P.ni, P.nj, P.nk };
     double fp[3], fq[3], fr[3];
@@ -476,6 +491,8 @@ __global__ void unpack_occ_kernel(const uint32_t* __restrict__ bits, int64_t n_b
         out[i] = ((bits[i >> 5] >> (i & 31)) & 1u) ? 1.f : 0.f;
 }
 
+#include "g3d_tdf_exact.cuh"
+
 int grid_for(int64_t n, int block, int max_blocks)
 {
     int64_t g = (n + block - 1) / block;
@@ -562,7 +579,7 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
     prof_mark(ST_FILL, stream);
     if (total_tris > 0) {
         tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status);
+            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr);
         prof_mark(ST_PREP, stream);
         tdf_init_kernel<<<grid_for(total_tris * 32, 256, sms * 32), 256, 0, stream>>>(
             w.tri, w.box, tri_off, total_tris, p, w.key, far, cnt);
@@ -576,6 +593,60 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
             if (rc != G3D_OK) return rc;
             prof_mark(ST_SWEEP, stream);
         }
+    }
+    tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
+        w.key, w.parity, vert_off, tri_off, n_mesh, p, out, 1);
+    prof_mark(ST_FINAL, stream);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+size_t tdf_exact_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
+{
+    return exact::carve(nullptr, n_mesh, total_tris, p).bytes;
+}
+
+int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
+                     const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
+                     int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
+                     void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
+    if (rc != G3D_OK) return rc;
+    if (n_mesh == 0) return G3D_OK;
+    exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
+    if (w.bytes > ws_bytes || (!ws && w.bytes)) {
+        set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+        return G3D_ERR_WORKSPACE;
+    }
+    const int nbx = (p.ni + 7) / 8, nby = (p.nj + 7) / 8, nbz = (p.nk + 7) / 8;
+    const int64_t nblocks = (int64_t)n_mesh * nbx * nby * nbz;
+    if (nblocks >= (int64_t)INT_MAX) { set_error("exact: too many blocks in one call (%lld)", (long long)nblocks); return G3D_ERR_INVALID; }
+    const int sms = sm_count();
+    const int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32;
+    const float far = (float)(p.ni + p.nj + p.nk) * p.dx;
+    union { float f; uint32_t u; } fb; fb.f = far;
+    const u64 init = ((u64)fb.u << 32) | 0xffffffffull;
+    // distances up to R matter: trunc is in output units (phi * out_scale)
+    float R = __builtin_inff();
+    if (p.trunc < 3.0e38f && p.out_scale > 0.f) R = p.trunc / p.out_scale * 1.0001f;
+
+    prof_begin(stream);
+    u64* cnt = prof_counters();
+    tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
+        w.key, n_mesh * nvox, init, w.parity, n_mesh * pw, out.status, n_mesh,
+        (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
+    prof_mark(ST_FILL, stream);
+    if (total_tris > 0) {
+        tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
+            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb);
+        prof_mark(ST_PREP, stream);
+        constexpr int NT = exact::kNT, TILE = exact::kTile;
+        const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
+        G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        exact::tdf_exact_kernel<NT, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+            w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
+        prof_mark(ST_EXACT, stream);
     }
     tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
         w.key, w.parity, vert_off, tri_off, n_mesh, p, out, 1);

@@ -1,0 +1,228 @@
+// g3d_tdf_exact.cuh -- "exact" mode: brute-force nearest triangle with truncation culling.
+// Included by g3d_tdf.cu (shares tdf_prep / tdf_finalize and the key format).
+//
+// The reference's far field is only approximate (makelevelset3.h:7-11: beyond the 1-cell band a
+// distance "might not be to the closest triangle"). This mode instead takes, for every voxel, the
+// true minimum of the reference's own float distance function over ALL triangles of the mesh --
+// bit-equal to the reference wherever the reference is exact (|d| <= 1 voxel, hence identical
+// occupancy), never larger elsewhere -- for every voxel whose distance can matter:
+//   * outside voxels (even x-ray parity): exact when d <= trunc (anything farther is clamped to
+//     trunc by load_df, dataset_loader.py:137-139) and reported as the reference's initial "far"
+//     value (ni+nj+nk)*dx otherwise;
+//   * inside voxels (odd parity): always exact (the negative side is never clamped).
+//
+// One CTA owns an 8x8x8 block of voxels of one mesh (16 warps x a 4x4x2 brick, one voxel per lane)
+// and streams the mesh's triangle bounding boxes through shared memory in tiles, double-buffered
+// with 1-D TMA bulk copies (cp.async.bulk + mbarrier): while the warps work on tile i, tile i+1 is
+// in flight.
+//   phase A  all threads: tile boxes vs the block's box with the block's static radius -> compacted
+//            survivor list in shared memory;
+//   phase B  each warp: survivors vs its brick's box with the brick's RUNNING bound (the largest
+//            current best distance among its 32 voxels, a warp-shuffle max-reduce), 32 at a time
+//            via ballot; every survivor is then evaluated by all 32 lanes (the triangle record is a
+//            broadcast load) with the reference's distance function and merged with
+//            (d, t) < (best, best_t) lexicographic order = "lowest triangle index wins ties".
+#pragma once
+
+namespace exact {
+
+constexpr int kNT = 512;
+constexpr int kTile = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// squared distance between two axis-aligned boxes (0 when they overlap); FMA is fine here, the
+// result only feeds a conservative comparison
+__device__ __forceinline__ float box_gap2(float4 alo, float4 ahi, V3 blo, V3 bhi)
+{
+    float gx = fmaxf(0.f, fmaxf(alo.x - bhi.x, blo.x - ahi.x));
+    float gy = fmaxf(0.f, fmaxf(alo.y - bhi.y, blo.y - ahi.y));
+    float gz = fmaxf(0.f, fmaxf(alo.z - bhi.z, blo.z - ahi.z));
+    return fmaf(gx, gx, fmaf(gy, gy, gz * gz));
+}
+
+// a NaN box (neutralised triangle) compares false and is culled; a NaN distance never wins
+__device__ __forceinline__ float bound2_of(float r) { return fmaf(r * r, 1.001f, 1e-12f); }
+
+template <int NT, int TILE>
+__global__ void __launch_bounds__(NT, 2)
+tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb,
+                 const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
+                 g3d_tdf_params P, float R, float far, int nbx, int nby, int nbz, u64* counter)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [2][TILE * 2]
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 2 * TILE * 32);    // [TILE]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_list + TILE);             // [2]
+    int* s_count = reinterpret_cast<int*>(s_bar + 2);                         // [2]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = nbx * nby * nbz;
+    const int mesh = blockIdx.x / nblk;
+    int b = blockIdx.x - mesh * nblk;
+    const int cbx = b % nbx; b /= nbx;
+    const int cby = b % nby, cbz = b / nby;
+    const int ni = P.ni, nj = P.nj, nk = P.nk;
+    const int64_t nvox = nvox_of(P);
+
+    // block = 8x8x8 nodes; warp -> 4x4x2 brick; lane -> node
+    const int bi0 = cbx * 8 + (warp & 1) * 4, bj0 = cby * 8 + ((warp >> 1) & 1) * 4, bk0 = cbz * 8 + (warp >> 2) * 2;
+    const int i = bi0 + (lane & 3), j = bj0 + ((lane >> 2) & 3), k = bk0 + (lane >> 4);
+    const bool valid = i < ni && j < nj && k < nk;
+    bool inside = false;
+    if (valid) {                                    // running parity along i (makelevelset3.cpp:174-182)
+        const uint32_t* par = parity + (int64_t)mesh * ((nvox + 31) / 32);
+        int64_t r0 = (int64_t)ni * (j + (int64_t)nj * k), r1 = r0 + i;
+        int cnt = 0;
+        for (int64_t w = r0 >> 5; w <= (r1 >> 5); ++w) {
+            uint32_t m = par[w];
+            if (w == (r0 >> 5)) m &= 0xffffffffu << (r0 & 31);
+            if (w == (r1 >> 5)) m &= 0xffffffffu >> (31 - (r1 & 31));
+            cnt += __popc(m);
+        }
+        inside = cnt & 1;
+    }
+    const V3 gx = node_pos(i, j, k, P);
+    float best = valid ? (inside ? __int_as_float(0x7f800000) : R) : 0.f;
+    uint32_t best_t = 0xffffffffu;
+
+    // boxes of the brick and of the block (node positions are monotone in the index)
+    const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
+    const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
+    const V3 blk_lo = node_pos(cbx * 8, cby * 8, cbz * 8, P);
+    const V3 blk_hi = node_pos(min(cbx * 8 + 7, ni - 1), min(cby * 8 + 7, nj - 1), min(cbz * 8 + 7, nk - 1), P);
+    const int any_inside = __syncthreads_or(inside ? 1 : 0);
+    const float blk_bound2 = any_inside ? __int_as_float(0x7f800000) : bound2_of(R);
+
+    const int64_t t0 = tri_off[mesh];
+    const int T = (int)(tri_off[mesh + 1] - t0);
+    const float4* Tm = tri + 4 * t0;
+    const float4* Bm = aabb + 2 * t0;
+    const int ntile = (T + TILE - 1) / TILE;
+    u64 n_pairs = 0, n_tests = 0;
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        s_count[0] = s_count[1] = 0;
+    }
+    __syncthreads();
+    if (tid == 0 && ntile > 0) {
+        uint32_t bytes = (uint32_t)min(TILE, T) * 32u;
+        mbar_expect_tx(&s_bar[0], bytes);
+        bulk_g2s(s_box, Bm, bytes, &s_bar[0]);
+    }
+    for (int it = 0; it < ntile; ++it) {
+        const int st = it & 1;
+        const int tile_base = it * TILE;
+        const int tn = min(TILE, T - tile_base);
+        if (tid == 0 && it + 1 < ntile) {           // stage st^1 was released by the barrier ending iteration it-1
+            uint32_t bytes = (uint32_t)min(TILE, T - (tile_base + TILE)) * 32u;
+            mbar_expect_tx(&s_bar[st ^ 1], bytes);
+            bulk_g2s(s_box + (st ^ 1) * TILE * 2, Bm + 2 * (int64_t)(tile_base + TILE), bytes, &s_bar[st ^ 1]);
+        }
+        mbar_wait(&s_bar[st], (it >> 1) & 1);
+        const float4* box = s_box + st * TILE * 2;
+
+        // ---- phase A: block-level cull, compacted with one shared atomic per warp
+        for (int q0 = warp * 32; q0 < tn; q0 += NT) {
+            int q = q0 + lane;
+            bool pass = false;
+            if (q < tn) {
+                pass = box_gap2(box[2 * q], box[2 * q + 1], blk_lo, blk_hi) <= blk_bound2;
+                ++n_tests;
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_count[st], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)q;
+            }
+        }
+        __syncthreads();
+        const int nlist = s_count[st];
+        if (tid == 0) s_count[st ^ 1] = 0;          // nobody touches the other counter until the next iteration
+
+        // ---- phase B: brick-level cull with the running bound, then the distance evaluations
+        for (int l0 = 0; l0 < nlist; l0 += 32) {
+            float bound = best;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, d));
+            const float bound2 = bound2_of(bound);
+            int q = -1;
+            bool pass = false;
+            if (l0 + lane < nlist) {
+                q = (int)s_list[l0 + lane];
+                pass = box_gap2(box[2 * q], box[2 * q + 1], brick_lo, brick_hi) <= bound2;
+                ++n_tests;
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, pass);
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t t = (uint32_t)(tile_base + __shfl_sync(0xffffffffu, q, src));
+                const float d = point_triangle_distance(gx, load_trirec(Tm + 4 * (int64_t)t));
+                if (d < best || (d == best && t < best_t)) { best = d; best_t = t; }
+                n_pairs += valid ? 1 : 0;
+            }
+        }
+        __syncthreads();                            // stage st and the list are free again
+    }
+    if (valid) {
+        float phi = (best_t == 0xffffffffu) ? far : best;
+        key[(int64_t)mesh * nvox + (i + (int64_t)ni * (j + (int64_t)nj * k))] = ((u64)__float_as_uint(phi) << 32) | best_t;
+    }
+    if (counter) {
+        if (n_pairs) atomicAdd(counter + 2, n_pairs);
+        if (n_tests) atomicAdd(counter + 3, n_tests);
+    }
+}
+
+struct Ws {
+    float4* tri; float4* aabb; int4* box; u64* key; uint32_t* parity; size_t bytes;
+};
+
+inline Ws carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
+{
+    Ws w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+    int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32;
+    w.tri = (float4*)take((size_t)total_tris * 64);
+    w.aabb = (float4*)take((size_t)total_tris * 32);
+    w.box = (int4*)take((size_t)total_tris * 16);
+    w.key = (u64*)take((size_t)n_mesh * nvox * 8);
+    w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace exact

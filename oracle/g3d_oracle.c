@@ -10,7 +10,7 @@
  * Parity pinning: the reference ships no golden vectors for this path
  * (SURVEY.md section 4/8c), so this restatement is pinned against the
  * reference's own sources compiled in place (oracle/_ref/libg3d_ref.so, see
- * oracle/Makefile + oracle/ref_shim.cpp); tests/test_oracle_vs_ref.py compares
+ * oracle/Makefile + oracle/ref_shim.cpp); tests/test_oracle.py compares
  * the two bit-for-bit whenever oracle/_ref exists.
  *
  * Build: gcc -O2 -ffp-contract=off (no -march, no fast-math) so that every
@@ -326,4 +326,32 @@ void g3d_oracle_occupancy(const float *sdf, int64_t n, float trunc, float res, u
 {
     float thr = trunc * res;
     for (int64_t i = 0; i < n; ++i) occ[i] = fabsf(sdf[i]) <= thr;
+}
+
+/*
+ * Brute force: for every node the minimum of the reference's distance function
+ * (makelevelset3.cpp:20-41) over ALL triangles, lowest triangle index on ties.
+ * This is what make_level_set3 would return if its band covered the whole grid;
+ * it is the checker for the product's "exact" mode.
+ */
+void g3d_oracle_brute_force(const uint32_t *tri, int64_t ntri, const float *x, const float *origin,
+                            float dx, int ni, int nj, int nk, float *phi, int32_t *closest_tri)
+{
+    float far = (ni + nj + nk) * dx;
+    for (int k = 0; k < nk; ++k)
+        for (int j = 0; j < nj; ++j)
+            for (int i = 0; i < ni; ++i) {
+                float gx[3] = { i * dx + origin[0], j * dx + origin[1], k * dx + origin[2] };
+                float best = far;
+                int32_t bt = -1;
+                for (int64_t t = 0; t < ntri; ++t) {
+                    float d = g3d_oracle_point_triangle_distance(gx, x + 3 * (size_t)tri[3 * t],
+                                                                 x + 3 * (size_t)tri[3 * t + 1],
+                                                                 x + 3 * (size_t)tri[3 * t + 2]);
+                    if (d < best) { best = d; bt = (int32_t)t; }
+                }
+                size_t q = (size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)k);
+                phi[q] = best;
+                if (closest_tri) closest_tri[q] = bt;
+            }
 }

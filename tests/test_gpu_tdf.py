@@ -199,3 +199,56 @@ def test_full_size_batch_properties(g3d, oracle):
         assert np.array_equal(_bits(one), _bits(sdf[m]))
     want = _oracle_full(oracle, V[voff[7]:voff[8]], T[toff[7]:toff[8]], 32)
     assert np.array_equal(_bits(sdf[7]), _bits(want["sdf"]))
+
+
+@pytest.mark.parametrize("n,dim,seed", [(5, 32, 40), (3, 16, 41), (4, 20, 42)])
+def test_exact_mode_vs_brute_force_oracle(g3d, oracle, n, dim, seed):
+    """Exact mode = true minimum of the reference's distance function over all triangles wherever it can matter:
+    outside voxels within the truncation, and every inside voxel; 'far' elsewhere. Bit-exact, ties to the lowest
+    triangle index. Occupancy (|d| <= 1) equals the reference's (its band is exact there)."""
+    from generate3d_b200 import dfgen
+    v, t = S.table_mesh(n, seed)
+    g = oracle.dfgen_geometry(dim)
+    bf, bt = oracle.brute_force(t, v, g["origin"], g["dx"], dim, dim, dim)
+    faithful = _oracle_full(oracle, v, t, dim)
+    got = _run(dfgen, [(v, t)], dim, mode="exact")
+    assert got["status"][0] == 0
+    sdf = got["sdf"][0]
+    inside = np.signbit(faithful["sdf"])
+    assert np.array_equal(np.signbit(sdf), inside)                           # same x-ray parity signs
+    want = bf * np.float32(dim)
+    far = np.float32(3 * dim * g["dx"] * dim)
+    near = inside | (want <= 3.0)
+    assert np.array_equal(_bits(np.abs(sdf)[near]), _bits(want[near]))       # exact where it matters
+    assert np.array_equal(got["closest_tri"][0][near], bt[near])
+    beyond = ~inside & (want > 3.0 * 1.001)
+    assert np.all(sdf[beyond] == far) and np.all(got["closest_tri"][0][beyond] == -1)
+    assert np.array_equal(got["occ_f32"][0].astype(np.uint8), oracle.occupancy(faithful["sdf"]))
+    assert np.all(np.abs(sdf)[near] <= np.abs(faithful["sdf"])[near])        # exact <= reference-faithful
+    tdf = oracle.load_df_clamp(np.where(near, np.copysign(want, faithful["sdf"]), far), 3.0)
+    assert np.array_equal(_bits(got["tdf"][0]), _bits(tdf))
+
+
+def test_exact_mode_untruncated_and_ragged(g3d, oracle):
+    """trunc = inf turns exact mode into a full brute force (branch-and-bound only); ragged batch + bad mesh."""
+    from generate3d_b200 import dfgen, _lib
+    meshes = [S.table_mesh(3, 50), S.table_mesh(2, 51, scale=0.7, rot_y=1.0)]
+    bv, bt_ = S.table_mesh(2, 52)
+    bt_ = bt_.copy(); bt_[1, 2] = 99999
+    meshes.append((bv, bt_))
+    p, _ = dfgen.dfgen_geometry(16)
+    p.trunc, p.occ_thresh, p.mode = float("inf"), 1.0, _lib.MODE_EXACT
+    voff, toff = [0], [0]
+    for v, t in meshes:
+        voff.append(voff[-1] + len(v)); toff.append(toff[-1] + len(t))
+    V = np.concatenate([m[0] for m in meshes]); T = np.concatenate([m[1] for m in meshes])
+    r = dfgen.tdf_batch_params(V, np.asarray(voff), T, np.asarray(toff), p, ("sdf", "closest_tri", "status"))
+    assert r["status"].cpu().tolist() == [0, 0, 1]
+    g = oracle.dfgen_geometry(16)
+    for m, (v, t) in enumerate(meshes):
+        if m == 2:
+            t = np.delete(t, 1, 0)
+        bf, bt = oracle.brute_force(t, v, g["origin"], g["dx"], 16, 16, 16)
+        assert np.array_equal(_bits(np.abs(r["sdf"][m].cpu().numpy())), _bits(bf * np.float32(16))), m
+        if m != 2:
+            assert np.array_equal(r["closest_tri"][m].cpu().numpy(), bt), m
