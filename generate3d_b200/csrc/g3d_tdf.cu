@@ -46,6 +46,7 @@ struct TdfWs {
     float4*   tri;          // 4 x float4 per triangle: TriRec (g3d_ptd.cuh)
     int4*     box;          // i0|i1<<16, j0|j1<<16, k0|k1<<16, mesh
     u64*      key;
+    uint8_t*  chg;          // per node: 0 = closest_tri set by the band init, s+1 = last changed in sweep s
     uint32_t* parity;
     uint32_t* order;        // packed a | b<<10 | c<<20, grouped by level
     int32_t*  level_start;  // [nlev + 1]
@@ -71,6 +72,7 @@ TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params
     w.tri = (float4*)take((size_t)total_tris * 64);
     w.box = (int4*)take((size_t)total_tris * 16);
     w.key = (u64*)take((size_t)n_mesh * nvox * 8);
+    w.chg = (uint8_t*)take((size_t)n_mesh * nvox);
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
     w.order = (uint32_t*)take((size_t)nsweep * 4);
     w.level_start = (int32_t*)take((size_t)(nlev_of(p) + 2) * 4);
@@ -226,13 +228,37 @@ __device__ __forceinline__ V3 node_pos(int i, int j, int k, const g3d_tdf_params
              add(mul((float)k, P.dx), P.origin[2]) };
 }
 
+// One warp per triangle walks the triangle's band box 32 nodes at a time. A node farther from the
+// triangle's bounding box than its current phi cannot win (nor tie) the `<`, so it is dropped
+// before the expensive evaluation (about 9 in 10 are); the survivors of successive triangles are
+// collected in a warp-private queue and evaluated 32 at a time, one (node, triangle) pair per lane.
+// The margin (0.1 % on the squared distance) dwarfs the rounding of the float distance function;
+// reading a stale, larger phi only makes the test less aggressive.
+__device__ __forceinline__ void init_eval_item(uint32_t t, uint32_t pos, const float4* __restrict__ tri,
+                                               const int4* __restrict__ box, const int64_t* __restrict__ tri_off,
+                                               const g3d_tdf_params& P, u64* key, int64_t nvox, float far)
+{
+    const int i = pos & 1023u, j = (pos >> 10) & 1023u, k = pos >> 20;
+    const int mesh = __ldg(box + t).w;
+    const float d = point_triangle_distance(node_pos(i, j, k, P), load_trirec(tri + 4 * (int64_t)t));
+    u64* kp = key + (int64_t)mesh * nvox + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k));
+    const float cur = __uint_as_float((uint32_t)(__ldca(kp) >> 32));
+    // d < far mirrors the very first `d < phi`; d <= cur lets an equal distance with a LOWER
+    // triangle index through, as the serial loop would
+    if (d < far && d <= cur) atomicMin(kp, ((u64)__float_as_uint(d) << 32) | (uint32_t)(t - tri_off[mesh]));
+}
+
 __global__ void __launch_bounds__(256)
 tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
                 const int64_t* __restrict__ tri_off, int64_t total_tris, g3d_tdf_params P,
                 u64* __restrict__ key, float far, u64* counter)
 {
+    __shared__ uint32_t s_qt[8][64], s_qp[8][64];
     u64 n_eval = 0;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* qt = s_qt[wib];
+    uint32_t* qp = s_qp[wib];
+    int qn = 0;                                     // queue fill, warp-uniform
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t nvox = nvox_of(P);
@@ -241,21 +267,64 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
         int i0 = b.x & 0xffff, i1 = b.x >> 16, j0 = b.y & 0xffff, j1 = b.y >> 16, k0 = b.z & 0xffff, k1 = b.z >> 16;
         int bi = i1 - i0 + 1, bj = j1 - j0 + 1, bk = k1 - k0 + 1;
         if (bi <= 0 || bj <= 0 || bk <= 0) continue;
-        const TriRec rec = load_trirec(tri + 4 * t);
-        uint32_t tl = (uint32_t)(t - tri_off[b.w]);
-        u64* K = key + (int64_t)b.w * nvox;
-        int n = bi * bj * bk;
-        for (int q = lane; q < n; q += 32) {
-            int i = i0 + q % bi, r = q / bi;
-            int j = j0 + r % bj, k = k0 + r / bj;
-            float d = point_triangle_distance(node_pos(i, j, k, P), rec);
-            ++n_eval;
-            u64* kp = K + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k));
-            float cur = __uint_as_float((uint32_t)(*(volatile u64*)kp >> 32));
-            // d < far mirrors the very first `d < phi`; d <= cur lets an equal
-            // distance with a LOWER triangle index through, as the serial loop would
-            if (d < far && d <= cur) atomicMin(kp, ((u64)__float_as_uint(d) << 32) | tl);
+        const float4 v1 = __ldg(tri + 4 * t), v2 = __ldg(tri + 4 * t + 1), v3 = __ldg(tri + 4 * t + 2);
+        const float lox = fminf(v1.x, fminf(v2.x, v3.x)), hix = fmaxf(v1.x, fmaxf(v2.x, v3.x));
+        const float loy = fminf(v1.y, fminf(v2.y, v3.y)), hiy = fmaxf(v1.y, fmaxf(v2.y, v3.y));
+        const float loz = fminf(v1.z, fminf(v2.z, v3.z)), hiz = fmaxf(v1.z, fmaxf(v2.z, v3.z));
+        // a non-finite vertex gives NaN distances, which never win: nothing to do for this triangle
+        if (!(fabsf(v1.x + v1.y + v1.z + v2.x + v2.y + v2.z + v3.x + v3.y + v3.z) < 3.0e38f)) continue;
+        const u64* K = key + (int64_t)b.w * nvox;
+        const int n = bi * bj * bk;
+        const float rbi = 1.0f / (float)bi, rbj = 1.0f / (float)bj;
+        for (int q0 = 0; q0 < n; q0 += 32) {
+            const int q = q0 + lane;
+            bool pass = false;
+            uint32_t pos = 0;
+            if (q < n) {
+                // q = i' + bi*(j' + bj*k'). For q < 2^20 the float product (q + 0.5) * fl(1/bi) is within
+                // q * 2^-22 < 0.5/bi of the true quotient, whose fraction is at least 0.5/bi away from an
+                // integer, so truncation gives the exact quotient without an integer division.
+                int r, k;
+                if (n <= (1 << 20)) {
+                    r = (int)(((float)q + 0.5f) * rbi);
+                    k = (int)(((float)r + 0.5f) * rbj);
+                } else {
+                    r = q / bi;
+                    k = r / bj;
+                }
+                const int i = i0 + (q - r * bi);
+                const int j = j0 + (r - k * bj);
+                k += k0;
+                const V3 gx = node_pos(i, j, k, P);
+                const float cur = __uint_as_float((uint32_t)(__ldca(K + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k))) >> 32));
+                const float ex = fmaxf(0.f, fmaxf(lox - gx.x, gx.x - hix));
+                const float ey = fmaxf(0.f, fmaxf(loy - gx.y, gx.y - hiy));
+                const float ez = fmaxf(0.f, fmaxf(loz - gx.z, gx.z - hiz));
+                pass = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(cur * cur, 1.001f, 1e-12f));
+                pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                if (pass) {
+                    const int w = qn + __popc(m & ((1u << lane) - 1u));
+                    qt[w] = (uint32_t)t;
+                    qp[w] = pos;
+                }
+                qn += __popc(m);
+                if (qn >= 32) {
+                    __syncwarp();
+                    qn -= 32;
+                    init_eval_item(qt[qn + lane], qp[qn + lane], tri, box, tri_off, P, key, nvox, far);
+                    ++n_eval;
+                    __syncwarp();
+                }
+            }
         }
+    }
+    __syncwarp();
+    if (lane < qn) {
+        init_eval_item(qt[lane], qp[lane], tri, box, tri_off, P, key, nvox, far);
+        ++n_eval;
     }
     if (counter && n_eval) atomicAdd(counter, n_eval);
 }
@@ -289,46 +358,75 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 }
 
 // ----------------------------------------------------------------- sweep ----
-// One CTA per mesh. Per level each thread owns one node: it reads the closest_tri of
-// its 7 upwind neighbours and decides which of them need a distance evaluation. A
-// candidate equal to the node's own triangle, or to an earlier candidate, re-evaluates
-// to a distance that cannot pass the strict `<` (it equals or exceeds the current
-// phi), so it is skipped -- about 2/3 of the reference's evaluations.
-// The surviving (node, triangle) pairs are unevenly spread over the lanes, so each warp
-// pushes them into a private shared-memory queue, evaluates the queue densely (one pair
-// per lane), and the owners then replay the results in the reference's neighbour order.
+// One CTA per mesh. Per level each thread owns one node and must replay, in the reference's
+// order, "if (d(node, closest_tri(nb)) < phi) take it" for its 7 upwind neighbours. Three
+// observations remove most of that work without changing a single bit of the result
+// (d is a pure function of (node, triangle) and phi only ever decreases, so a comparison
+// that failed once fails for ever):
+//   1. a candidate equal to the node's own triangle, or to an earlier candidate of the same
+//      visit, cannot pass the strict `<`;
+//   2. a neighbour whose closest_tri has not changed since this node last examined it (in an
+//      earlier sweep that had the same neighbour upwind) cannot pass either. `chg` records the
+//      sweep in which each node last changed; s_prev[s][r] is the last earlier sweep in which
+//      slot r of sweep s pointed at the same absolute neighbour. The whole second pass of a
+//      converged field is skipped this way. Nodes on the grid boundary are not part of every
+//      sweep lattice, so they take no shortcut of this kind;
+//   3. the surviving (node, triangle) pairs are unevenly spread over the lanes, so each warp
+//      pushes them into a private shared-memory queue, evaluates the queue densely (one pair
+//      per lane), and the owners then replay the results in neighbour order.
 constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
+
+__device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
+{
+    const int q8 = s & 7;                           // cpp:163-172, pass 0 then pass 1
+    di = (q8 & 1) ? -1 : 1;
+    dj = (q8 == 0 || q8 == 2 || q8 == 5 || q8 == 7) ? 1 : -1;
+    dk = (q8 == 0 || q8 == 3 || q8 == 4 || q8 == 7) ? 1 : -1;
+}
 
 template <int NT>
 __global__ void __launch_bounds__(NT)
-tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
+tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                  const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
                  int lev_words, g3d_tdf_params P, u64* counter)
 {
     u64 n_eval = 0;
     extern __shared__ uint32_t s_mem[];
+    __shared__ int s_prev[16][8];
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* q_tri = s_mem + lev_words + warp * (3 * kSweepQueue);
     uint32_t* q_pos = q_tri + kSweepQueue;
     float* q_res = reinterpret_cast<float*>(q_pos + kSweepQueue);
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
+    if (threadIdx.x < 16 * 8) {
+        // slot r+1 = (ai, aj, ak) bit mask of the axes on which the neighbour is one step upwind
+        const int s = threadIdx.x >> 3, r = threadIdx.x & 7, a = r + 1;
+        int di, dj, dk, thr = -1;
+        sweep_dir(s, di, dj, dk);
+        for (int sp = 0; sp < s; ++sp) {
+            int ei, ej, ek;
+            sweep_dir(sp, ei, ej, ek);
+            if ((!(a & 1) || ei == di) && (!(a & 2) || ej == dj) && (!(a & 4) || ek == dk)) thr = sp + 1;
+        }
+        s_prev[s][r] = thr;                         // examine nb iff chg[nb] > thr
+    }
     __syncthreads();
     const int mesh = blockIdx.x;
     const int64_t nvox = nvox_of(P);
     u64* K = key + (int64_t)mesh * nvox;
+    uint8_t* G = chg + (int64_t)mesh * nvox;
     const int* Klo = (const int*)K;                // low word of each key = closest_tri
     const float4* T = tri + 4 * tri_off[mesh];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int sj = ni, sk = ni * nj;
 
     for (int s = 0; s < 16; ++s) {
-        // cpp:163-172 sweep directions, pass 0 then pass 1
-        const int q8 = s & 7;
-        const int di = (q8 & 1) ? -1 : 1;
-        const int dj = (q8 == 0 || q8 == 2 || q8 == 5 || q8 == 7) ? 1 : -1;
-        const int dk = (q8 == 0 || q8 == 3 || q8 == 4 || q8 == 7) ? 1 : -1;
+        int di, dj, dk;
+        sweep_dir(s, di, dj, dk);
         const int oi = di, oj = dj * sj, ok = dk * sk;
+        const int t0 = s_prev[s][0], t1 = s_prev[s][1], t2 = s_prev[s][2], t3 = s_prev[s][3], t4 = s_prev[s][4],
+                  t5 = s_prev[s][5], t6 = s_prev[s][6];
         for (int L = 0; L < nlev; ++L) {
             const int beg = s_lev[L], end = s_lev[L + 1];
             for (int qb = beg + warp * 32; qb < end; qb += NT) {
@@ -345,20 +443,35 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
                     n = i + sj * j + sk * k;
                     // the 7 upwind neighbours in the order of cpp:72-78
-                    c0 = Klo[2 * (n - oi)]; c1 = Klo[2 * (n - oj)]; c2 = Klo[2 * (n - oi - oj)];
-                    c3 = Klo[2 * (n - ok)]; c4 = Klo[2 * (n - oi - ok)]; c5 = Klo[2 * (n - oj - ok)];
-                    c6 = Klo[2 * (n - oi - oj - ok)];
-                    u64 kv = K[n];
-                    phi = __uint_as_float((uint32_t)(kv >> 32));
-                    ct = (int)(uint32_t)kv;
-                    need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
-                    need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
-                    need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
-                    need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
-                    need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
-                    need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
-                    need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                    const int n0 = n - oi, n1 = n - oj, n2 = n - oi - oj, n3 = n - ok, n4 = n - oi - ok,
+                              n5 = n - oj - ok, n6 = n - oi - oj - ok;
+                    const bool interior = i > 0 && i < ni - 1 && j > 0 && j < nj - 1 && k > 0 && k < nk - 1;
+                    uint32_t look = 127u;
+                    if (interior)
+                        look = ((int)G[n0] > t0 ? 1u : 0u) | ((int)G[n1] > t1 ? 2u : 0u) | ((int)G[n2] > t2 ? 4u : 0u) |
+                               ((int)G[n3] > t3 ? 8u : 0u) | ((int)G[n4] > t4 ? 16u : 0u) | ((int)G[n5] > t5 ? 32u : 0u) |
+                               ((int)G[n6] > t6 ? 64u : 0u);
+                    if (look) {
+                        if (look & 1u) c0 = Klo[2 * n0];
+                        if (look & 2u) c1 = Klo[2 * n1];
+                        if (look & 4u) c2 = Klo[2 * n2];
+                        if (look & 8u) c3 = Klo[2 * n3];
+                        if (look & 16u) c4 = Klo[2 * n4];
+                        if (look & 32u) c5 = Klo[2 * n5];
+                        if (look & 64u) c6 = Klo[2 * n6];
+                        u64 kv = K[n];
+                        phi = __uint_as_float((uint32_t)(kv >> 32));
+                        ct = (int)(uint32_t)kv;
+                        need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
+                        need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
+                        need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
+                        need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
+                        need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
+                        need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
+                        need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                    }
                 }
+                if (!__any_sync(0xffffffffu, need != 0)) continue;
                 // warp-exclusive prefix of the per-lane work counts
                 const int cnt = __popc(need);
                 int incl = cnt;
@@ -368,7 +481,6 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     if (lane >= d) incl += v;
                 }
                 const int W = __shfl_sync(0xffffffffu, incl, 31);
-                if (W == 0) continue;
                 const int off = incl - cnt;
                 {
                     int w = off;
@@ -399,7 +511,10 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     if (need & 16u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c4; changed = true; } }
                     if (need & 32u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c5; changed = true; } }
                     if (need & 64u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c6; changed = true; } }
-                    if (changed) K[n] = ((u64)__float_as_uint(phi) << 32) | (uint32_t)ct;
+                    if (changed) {
+                        K[n] = ((u64)__float_as_uint(phi) << 32) | (uint32_t)ct;
+                        G[n] = (uint8_t)(s + 1);
+                    }
                 }
             }
             __syncthreads();
@@ -511,7 +626,7 @@ int launch_sweep_nt(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off
     const int lev_words = (nlev + 1 + 3) & ~3;
     const size_t smem = (size_t)(lev_words + (NT / 32) * 3 * kSweepQueue) * 4;
     G3D_CUDA_TRY(cudaFuncSetAttribute(tdf_sweep_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tdf_sweep_kernel<NT><<<n_mesh, NT, smem, stream>>>(w.key, w.tri, tri_off, w.order, w.level_start, nlev, lev_words, p, cnt);
+    tdf_sweep_kernel<NT><<<n_mesh, NT, smem, stream>>>(w.key, w.chg, w.tri, tri_off, w.order, w.level_start, nlev, lev_words, p, cnt);
     return G3D_OK;
 }
 
@@ -573,6 +688,7 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
 
     prof_begin(stream);
     u64* cnt = prof_counters();
+    G3D_CUDA_TRY(cudaMemsetAsync(w.chg, 0, (size_t)n_mesh * nvox, stream));
     tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
         w.key, n_mesh * nvox, init, w.parity, n_mesh * pw, out.status, n_mesh,
         (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
