@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="meshes in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-mode", action="store_true")
     return ap.parse_args()
 
 
@@ -258,6 +259,44 @@ def run_b200(args, rank, world, local):
         "traffic": None,
     }
 
+    # ---- the other TDF mode, same batch, fewer steps: rides along under "other_mode"
+    other = "exact" if args.mode == "faithful" else "faithful"
+    other_mode = None
+    if not args.no_other_mode:
+        def other_step(o):
+            return dfgen.tdf_batch(dV, dvoff, dT, dtoff, dim=DIM, trunc=TRUNC, mode=other, outputs=outputs, out=o)
+        _lib.check(L.g3d_profile_enable(2))
+        oo = other_step(None)
+        torch.cuda.synchronize()
+        _lib.check(L.g3d_profile_read(None, ev))
+        oev = {"init": int(ev[0]), "sweep": int(ev[1]), "exact_pairs": int(ev[2]), "exact_box_tests": int(ev[3])}
+        _lib.check(L.g3d_profile_enable(1))
+        other_step(oo)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ostage = np.zeros(8)
+        nst = max(2, args.steps // 2)
+        o0.record()
+        for _ in range(nst):
+            other_step(oo)
+            _lib.check(L.g3d_profile_read(sm, None))
+            ostage += np.frombuffer(sm, np.float32)
+        o1.record()
+        barrier()
+        oms = shard.all_reduce_max(o0.elapsed_time(o1) / nst, dev)
+        ostage /= nst
+        okern = "exact" if other == "exact" else "sweep"
+        okms = float(ostage[6] if other == "exact" else ostage[4])
+        onev = oev["exact_pairs"] if other == "exact" else oev["sweep"]
+        oach = FLOP_PER_EVAL * onev / (okms * 1e-3) / 1e12 if okms else 0.0
+        other_mode = {"mode": other, "value": total_vox / (oms * 1e-3), "unit": "voxels/s", "ms_per_step": oms, "steps": nst,
+                      "stages_ms": {n: round(float(x), 4) for n, x in zip(names, ostage) if x > 0}, "evals_per_step": oev,
+                      "roofline": {"kernel": "tdf_%s_kernel" % okern, "bound": "fp32", "achieved": oach, "peak": float(tf.value),
+                                   "unit": "TFLOP/s", "frac": oach / float(tf.value) if tf.value else None,
+                                   "evals_per_launch": onev, "kernel_ms": okms}}
+        tdf_launches += (4 if other == "exact" else 6) * (nst + 2)
+        del oo
+
     # ---- raycast: configs[1] (20 views 256^2, one launch) and a batched leg (> L2) for the HBM roofline
     d20, p20 = S.depth_views(20, 256, 256)
     dd20, dp20 = torch.from_numpy(d20).to(dev), torch.from_numpy(p20).to(dev)
@@ -352,7 +391,7 @@ def run_b200(args, rank, world, local):
                        "trunc": TRUNC, "mode": args.mode, "outputs": list(outputs),
                        "l2": "inputs %.0f MB + outputs %.0f MB per step, larger than the 126 MB L2 (no explicit flush)" % (input_mb, M * DIM ** 3 * 12.125 / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": tdf_launches + ray_launches, "roofline": roofline,
-            "cpu_baseline": cpu, "stages_ms": stages_ms, "evals_per_step": evals, "raycast": raycast,
+            "cpu_baseline": cpu, "stages_ms": stages_ms, "evals_per_step": evals, "other_mode": other_mode, "raycast": raycast,
             "pair_rate_nominal_per_s": world * M * DIM ** 3 * 60 * args.n ** 2 / (ms_step * 1e-3),
         }
         print(json.dumps(line), flush=True)

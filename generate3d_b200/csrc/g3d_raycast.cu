@@ -7,16 +7,19 @@
 // Here one CTA handles (view, z-slab):
 //
 //  1. the u8 depth raster is read ONCE with 16-byte loads and reduced to a
-//     `depth > 0` bit mask in shared memory (H x W/32 words; 8 KB at 256^2);
+//     `depth > 0` bit mask in shared memory (H x W/32 words; 8 KB at 256^2),
+//     plus a second mask holding the OR of every 4 consecutive rows;
 //  2. the corners are shared lattice points, so each of the (dim+1)^3 lattice
 //     points is projected once (7.3x fewer projections) with the reference's
 //     arithmetic: cam = pose @ (g2w @ p) accumulated k = 0..3 with one FMA per
 //     term (the association MKL sgemm uses for raytracing.py:64, pinned by the
-//     golden fixtures), y flipped, u = x*f/|z| + cx, round-half-even, clamp;
-//  3. each voxel takes min/max over its 8 lattice points and tests its box
-//     against the mask a row at a time (half-open, clipped to the image as
-//     numpy slicing does); a warp ballots 32 voxels into one output word, so
-//     the bit-packed grid is written without atomics.
+//     golden fixtures), y flipped, u = x*f/|z| + cx, round-half-even, clamp.
+//     Planes are projected one at a time and kept two at a time; per plane the
+//     4-corner min/max of every (x, y) cell is formed once with packed 16-bit
+//     SIMD min/max, so a voxel's box is two 8-byte loads and two instructions;
+//  3. each voxel tests its box against the masks 4 rows at a time (half-open,
+//     clipped to the image as numpy slicing does); a warp ballots 32 voxels
+//     into one output word, so the bit-packed grid is written without atomics.
 //
 // Roofline: HBM. Algorithmic bytes per view = H*W (depth, read once) + 64
 // (pose) + dim^3/8 (packed occupancy) = 69,696 B at 256^2, 266,304 B at 512^2.
@@ -56,17 +59,19 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
     const int z0 = blockIdx.y * zs;
     const int z1 = min(dim, z0 + zs);
     const int Wp = (W + 31) >> 5;
-    const int n = dim + 1;
-    uint32_t* mask = smem;                          // [H * Wp]
-    uint32_t* uv = smem + (size_t)H * Wp;           // [(z1-z0+1) * n * n]  u | v << 16
+    const int n = dim + 1, nn = n * n, d2 = dim * dim;
+    uint32_t* m1 = smem;                            // [H * Wp]  depth > 0, one bit per pixel
+    uint32_t* m4 = m1 + (size_t)H * Wp;             // [H * Wp]  OR of rows r .. r+3
+    uint32_t* lat = m4 + (size_t)H * Wp;            // [2][n*n]  projected lattice plane: u | v << 16
+    uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [2][dim*dim] (min2, max2) of a cell's 4 corners
     const uint8_t* D = depth + (size_t)view * H * W;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     // ---- 1. depth > 0 bit mask (depth == NULL: index map only)
     if (!depth) {
     } else if ((W & 31) == 0 && ((reinterpret_cast<uintptr_t>(D) & 15) == 0)) {
         const uint4* D4 = reinterpret_cast<const uint4*>(D);
-        uint16_t* m16 = reinterpret_cast<uint16_t*>(mask);
+        uint16_t* m16 = reinterpret_cast<uint16_t*>(m1);
         const int nvec = (H * W) >> 4;              // rows are whole words: vec v -> half-word v
         for (int v = tid; v < nvec; v += NT) {
             uint4 x = __ldg(D4 + v);
@@ -79,85 +84,116 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
             int row = w / Wp, c0 = (w - row * Wp) << 5;
             uint32_t b = 0;
             for (int c = 0; c < 32 && c0 + c < W; ++c) b |= (D[(size_t)row * W + c0 + c] != 0 ? 1u : 0u) << c;
-            mask[w] = b;
+            m1[w] = b;
         }
     }
+    __syncthreads();
+    if (depth)
+        for (int w = tid; w < H * Wp; w += NT) {
+            int row = w / Wp;
+            uint32_t b = m1[w];
+            if (row + 1 < H) b |= m1[w + Wp];
+            if (row + 2 < H) b |= m1[w + 2 * Wp];
+            if (row + 3 < H) b |= m1[w + 3 * Wp];
+            m4[w] = b;
+        }
 
-    // ---- 2. lattice projection
+    // ---- 2. lattice planes are projected once each and kept two at a time
     const float* P = pose + (size_t)view * 16;
     const float p00 = P[0], p01 = P[1], p02 = P[2], p03 = P[3];
     const float p10 = P[4], p11 = P[5], p12 = P[6], p13 = P[7];
     const float p20 = P[8], p21 = P[9], p22 = P[10], p23 = P[11];
-    const int nlat = (z1 - z0 + 1) * n * n;
-    for (int q = tid; q < nlat; q += NT) {
-        int lx = q % n, r = q / n;
-        int ly = r % n, lz = z0 + r / n;
+    auto project_plane = [&](int lz, uint32_t* out) {
         // grid_to_world @ corner: inv*x + (-0.5)*1 (raytracing.py:35-40,64)
-        float wx = __fadd_rn(__fmul_rn(inv_dim, (float)lx), -0.5f);
-        float wy = __fadd_rn(__fmul_rn(inv_dim, (float)ly), -0.5f);
-        float wz = __fadd_rn(__fmul_rn(inv_dim, (float)lz), -0.5f);
-        float camx = fmaf(p03, 1.f, fmaf(p02, wz, fmaf(p01, wy, __fmul_rn(p00, wx))));
-        float camy = fmaf(p13, 1.f, fmaf(p12, wz, fmaf(p11, wy, __fmul_rn(p10, wx))));
-        float camz = fmaf(p23, 1.f, fmaf(p22, wz, fmaf(p21, wy, __fmul_rn(p20, wx))));
-        float az = fabsf(camz);
-        float u = __fadd_rn(__fdiv_rn(__fmul_rn(camx, focal), az), cx);     // raytracing.py:71
-        float v = __fadd_rn(__fdiv_rn(__fmul_rn(-camy, focal), az), cy);    // :70,72
-        uv[q] = (uint32_t)round_clamp(u, clamp_max) | ((uint32_t)round_clamp(v, clamp_max) << 16);
-    }
+        const float wz = __fadd_rn(__fmul_rn(inv_dim, (float)lz), -0.5f);
+        for (int q = tid; q < nn; q += NT) {
+            int ly = q / n, lx = q - ly * n;
+            float wx = __fadd_rn(__fmul_rn(inv_dim, (float)lx), -0.5f);
+            float wy = __fadd_rn(__fmul_rn(inv_dim, (float)ly), -0.5f);
+            float camx = fmaf(p03, 1.f, fmaf(p02, wz, fmaf(p01, wy, __fmul_rn(p00, wx))));
+            float camy = fmaf(p13, 1.f, fmaf(p12, wz, fmaf(p11, wy, __fmul_rn(p10, wx))));
+            float camz = fmaf(p23, 1.f, fmaf(p22, wz, fmaf(p21, wy, __fmul_rn(p20, wx))));
+            float az = fabsf(camz);
+            float u = __fadd_rn(__fdiv_rn(__fmul_rn(camx, focal), az), cx);     // raytracing.py:71
+            float v = __fadd_rn(__fdiv_rn(__fmul_rn(-camy, focal), az), cy);    // :70,72
+            out[q] = (uint32_t)round_clamp(u, clamp_max) | ((uint32_t)round_clamp(v, clamp_max) << 16);
+        }
+    };
+    auto build_quads = [&](const uint32_t* in, uint2* out) {
+        // per cell (x, y) of the plane: packed (umin | vmin << 16, umax | vmax << 16) over its 4 corners
+        for (int q = tid; q < d2; q += NT) {
+            int y = q / dim, x = q - y * dim;
+            const uint32_t* c = in + y * n + x;
+            uint32_t a = c[0], b = c[1], e = c[n], f = c[n + 1];
+            out[q] = make_uint2(__vminu2(__vminu2(a, b), __vminu2(e, f)), __vmaxu2(__vmaxu2(a, b), __vmaxu2(e, f)));
+        }
+    };
+    project_plane(z0, lat);
     __syncthreads();
+    build_quads(lat, quad);
 
-    // ---- 3. per-voxel box test
-    const int d2 = dim * dim;
-    const int nv = (z1 - z0) * d2;
+    // ---- 3. slice by slice: project plane z+1, then test the voxels between planes z and z+1
     const long long nvox = (long long)d2 * dim;
     const long long pw = (nvox + 31) >> 5;
     const bool aligned = (d2 & 31) == 0;
-    const int lane = tid & 31;
-    for (int base = tid - lane; base < nv; base += NT) {
-        int q = base + lane;
-        bool valid = q < nv;
-        bool occ = false;
-        long long lin = (long long)z0 * d2 + q;
-        if (valid) {
-            int x = q % dim, r = q / dim;
-            int y = r % dim, zl = r / dim;
-            const uint32_t* c = uv + (zl * n + y) * n + x;
-            uint32_t umin = 0xffffu, vmin = 0xffffu, umax = 0, vmax = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint32_t p = c[(k & 1) + ((k >> 1) & 1) * n + (k >> 2) * n * n];
-                uint32_t pu = p & 0xffffu, pv = p >> 16;
-                umin = min(umin, pu); umax = max(umax, pu);
-                vmin = min(vmin, pv); vmax = max(vmax, pv);
-            }
-            if (index_map) {
-                long long* im = index_map + (long long)view * 4 * nvox + lin;   // raytracing.py:76-80
-                im[0] = umin; im[nvox] = vmin; im[2 * nvox] = umax; im[3 * nvox] = vmax;
-            }
-            // depth[vmin:vmax, umin:umax] > 0 with numpy's end clipping (raytracing.py:134)
-            int u0 = min((int)umin, W), u1 = min((int)umax, W);
-            int v0 = min((int)vmin, H), v1 = min((int)vmax, H);
-            if (depth && u1 > u0 && v1 > v0) {
-                int wa = u0 >> 5, wb = (u1 - 1) >> 5;
-                uint32_t ma = 0xffffffffu << (u0 & 31);
-                uint32_t mb = 0xffffffffu >> (31 - ((u1 - 1) & 31));
-                for (int row = v0; row < v1 && !occ; ++row) {
-                    const uint32_t* mr = mask + row * Wp;
-                    for (int w = wa; w <= wb; ++w) {
-                        uint32_t m = mr[w];
-                        if (w == wa) m &= ma;
-                        if (w == wb) m &= mb;
-                        if (m) { occ = true; break; }
+    for (int z = z0; z < z1; ++z) {
+        const int cur = (z - z0) & 1, nxt = cur ^ 1;
+        project_plane(z + 1, lat + nxt * nn);
+        __syncthreads();                            // plane z+1 projected; everyone is done with slice z-1
+        build_quads(lat + nxt * nn, quad + nxt * d2);
+        __syncthreads();
+        const uint2* qa = quad + cur * d2;
+        const uint2* qb = quad + nxt * d2;
+        for (int base = tid - lane; base < d2; base += NT) {
+            const int q = base + lane;
+            const bool valid = q < d2;
+            bool occ = false;
+            const long long lin = (long long)z * d2 + q;
+            if (valid) {
+                const uint2 A = qa[q], B = qb[q];
+                const uint32_t mn = __vminu2(A.x, B.x), mx = __vmaxu2(A.y, B.y);
+                const int umin = mn & 0xffffu, vmin = mn >> 16, umax = mx & 0xffffu, vmax = mx >> 16;
+                if (index_map) {
+                    long long* im = index_map + (long long)view * 4 * nvox + lin;   // raytracing.py:76-80
+                    im[0] = umin; im[nvox] = vmin; im[2 * nvox] = umax; im[3 * nvox] = vmax;
+                }
+                // depth[vmin:vmax, umin:umax] > 0 with numpy's end clipping (raytracing.py:134)
+                const int u0 = min(umin, W), u1 = min(umax, W);
+                const int v0 = min(vmin, H), v1 = min(vmax, H);
+                if (depth && u1 > u0 && v1 > v0) {
+                    const int wa = u0 >> 5, wb = (u1 - 1) >> 5;
+                    const uint32_t ma = 0xffffffffu << (u0 & 31);
+                    const uint32_t mb = 0xffffffffu >> (31 - ((u1 - 1) & 31));
+                    int row = v0;
+                    if (wa == wb) {                 // the usual case: the box spans one mask word
+                        const uint32_t mm = ma & mb;
+                        uint32_t hit = 0;
+                        for (; row + 4 <= v1; row += 4) hit |= m4[row * Wp + wa];
+                        for (; row < v1; ++row) hit |= m1[row * Wp + wa];
+                        occ = (hit & mm) != 0;
+                    } else {
+                        uint32_t hit = 0;
+                        for (; row + 4 <= v1; row += 4) {
+                            const uint32_t* mr = m4 + row * Wp;
+                            hit |= (mr[wa] & ma) | (mr[wb] & mb);
+                            for (int w = wa + 1; w < wb; ++w) hit |= mr[w];
+                        }
+                        for (; row < v1; ++row) {
+                            const uint32_t* mr = m1 + row * Wp;
+                            hit |= (mr[wa] & ma) | (mr[wb] & mb);
+                            for (int w = wa + 1; w < wb; ++w) hit |= mr[w];
+                        }
+                        occ = hit != 0;
                     }
                 }
+                if (occ_f32) occ_f32[(long long)view * nvox + lin] = occ ? 1.f : 0.f;
             }
-            if (occ_f32) occ_f32[(long long)view * nvox + lin] = occ ? 1.f : 0.f;
-        }
-        uint32_t word = __ballot_sync(0xffffffffu, occ);
-        if (occ_bits) {
-            uint32_t* ow = occ_bits + (long long)view * pw;
-            if (aligned) { if (lane == 0 && base < nv) ow[lin >> 5] = word; }
-            else if (occ) atomicOr(ow + (lin >> 5), 1u << (lin & 31));
+            const uint32_t word = __ballot_sync(0xffffffffu, occ);
+            if (occ_bits) {
+                uint32_t* ow = occ_bits + (long long)view * pw;
+                if (aligned) { if (lane == 0) ow[lin >> 5] = word; }
+                else if (occ) atomicOr(ow + (lin >> 5), 1u << (lin & 31));
+            }
         }
     }
 }
@@ -176,18 +212,16 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     if (!pose || (!depth && (occ_bits || occ_f32))) { set_error("raycast: null input"); return G3D_ERR_INVALID; }
     constexpr int NT = 512;
     const int n = dim + 1;
-    const size_t mask_bytes = (size_t)H * ((W + 31) / 32) * 4;
-    auto smem_for = [&](int zs) { return mask_bytes + (size_t)(zs + 1) * n * n * 4; };
-    // z-slab depth: small enough that the grid covers the GPU ~2x and the CTA fits
-    // several times per SM, large enough to amortise the per-CTA mask rebuild
-    int zs = dim;
-    const int target = 2 * sm_count();
-    while (zs > 1 && ((int64_t)n_view * ((dim + zs - 1) / zs) < target || smem_for(zs) > 72 * 1024)) zs = (zs + 1) / 2;
-    size_t smem = smem_for(zs);
+    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 2 + ((size_t)2 * n * n + 1) * 4 + (size_t)2 * dim * dim * 8;
     if (smem > 227 * 1024) {
         set_error("raycast: image %dx%d needs %zu bytes of shared memory (max 232448)", H, W, smem);
         return G3D_ERR_INVALID;
     }
+    // z-range per CTA: the whole grid when the batch alone fills the GPU (the mask is then built once per
+    // view), thinner slabs for small batches so that ~2 CTAs per SM exist
+    int zs = dim;
+    const int target = 2 * sm_count();
+    while (zs > 1 && (int64_t)n_view * ((dim + zs - 1) / zs) < target) zs = (zs + 1) / 2;
     G3D_CUDA_TRY(cudaFuncSetAttribute(raycast_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nvox = (int64_t)dim * dim * dim;
     if (occ_bits && ((dim * dim) & 31))
