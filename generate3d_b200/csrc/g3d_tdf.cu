@@ -92,6 +92,15 @@ __global__ void tdf_fill_kernel(u64* key, int64_t n_key, u64 init, uint32_t* par
     if (status) for (int64_t i = t0; i < n_mesh; i += stride) status[i] = 0;
 }
 
+__device__ __forceinline__ V3 node_pos(int i, int j, int k, const g3d_tdf_params& P)
+{
+    // Vec3f gx(i*dx+origin[0], ...) (cpp:139): int -> float, one mul, one add
+    return { add(mul((float)i, P.dx), P.origin[0]), add(mul((float)j, P.dx), P.origin[1]),
+             add(mul((float)k, P.dx), P.origin[2]) };
+}
+
+#include "g3d_tdf_exact.cuh"
+
 // ------------------------------------------------------------------ prep ----
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
@@ -145,7 +154,7 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
                 const uint32_t* __restrict__ tris, const int64_t* __restrict__ tri_off,
                 int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
                 int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status,
-                float4* __restrict__ aabb_out)
+                float4* __restrict__ aabb_out, float4* __restrict__ fast_out)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_tris) return;
@@ -159,7 +168,23 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
         float qnan = __int_as_float(0x7fc00000);
         tri_out[4 * t] = tri_out[4 * t + 1] = tri_out[4 * t + 2] = tri_out[4 * t + 3] = make_float4(qnan, qnan, qnan, qnan);
         box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
-        if (aabb_out) aabb_out[2 * t] = aabb_out[2 * t + 1] = make_float4(qnan, qnan, qnan, qnan);
+        if (aabb_out) {                            // same slot computation as below
+            const int64_t tbase = tri_off[m];
+            const uint64_t T = (uint64_t)(tri_off[m + 1] - tbase), tl = (uint64_t)(t - tbase);
+            uint64_t A = 40503u % (T ? T : 1);
+            for (;; ++A) {
+                uint64_t x = A, y = T;
+                while (y) { uint64_t r = x % y; x = y; y = r; }
+                if (x == 1 || T <= 1) break;
+            }
+            const int64_t slot = tbase + (int64_t)((tl * A) % (T ? T : 1));
+            // an inverted infinite box: infinitely far from everything (fmaxf would turn a NaN box into
+            // distance 0), and still carrying a valid triangle index for the case of an infinite bound
+            const float inf = __int_as_float(0x7f800000);
+            aabb_out[2 * slot] = make_float4(inf, inf, inf, __uint_as_float((uint32_t)tl));
+            aabb_out[2 * slot + 1] = make_float4(-inf, -inf, -inf, 0.f);
+        }
+        if (fast_out) for (int q = 0; q < 5; ++q) fast_out[5 * t + q] = make_float4(qnan, qnan, qnan, qnan);
         return;
     }
     const float* pp = verts + 3 * (v0 + ip);
@@ -167,18 +192,37 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
     const float* pr = verts + 3 * (v0 + ir);
     float xp[3] = { pp[0], pp[1], pp[2] }, xq[3] = { pq[0], pq[1], pq[2] }, xr[3] = { pr[0], pr[1], pr[2] };
     store_trirec(tri_out + 4 * t, make_trirec({ xp[0], xp[1], xp[2] }, { xq[0], xq[1], xq[2] }, { xr[0], xr[1], xr[2] }));
-    if (aabb_out) {                                // exact mode: world-space bounding box of the triangle
-        aabb_out[2 * t] = make_float4(fminf(xp[0], fminf(xq[0], xr[0])), fminf(xp[1], fminf(xq[1], xr[1])),
-                                      fminf(xp[2], fminf(xq[2], xr[2])), 0.f);
-        aabb_out[2 * t + 1] = make_float4(fmaxf(xp[0], fmaxf(xq[0], xr[0])), fmaxf(xp[1], fmaxf(xq[1], xr[1])),
-                                          fmaxf(xp[2], fmaxf(xq[2], xr[2])), 0.f);
-        // a non-finite vertex must poison the box (fminf/fmaxf drop NaNs) so the triangle is culled,
-        // exactly as its NaN distances never win in the reference
+    if (fast_out) exact::store_fastrec(fast_out + 5 * t, { xp[0], xp[1], xp[2] }, { xq[0], xq[1], xq[2] }, { xr[0], xr[1], xr[2] });
+    if (aabb_out) {
+        // exact mode: world-space bounding box of the triangle, stored at a pseudo-random position of the
+        // mesh's box array (p = tl * A mod T, A coprime with T) with the triangle's own index in lo.w.
+        // Streaming the boxes in that order makes every tile a uniform sample of the mesh, so a voxel's
+        // running minimum drops to its final value after a few tiles instead of creeping towards it along
+        // a face; fewer pairs survive the cull and far fewer set a new minimum. Ties are still broken by
+        // the ORIGINAL index, so the result does not depend on the order.
+        const int64_t tbase = tri_off[m];
+        const uint64_t T = (uint64_t)(tri_off[m + 1] - tbase), tl = (uint64_t)(t - tbase);
+        uint64_t A = 40503u % (T ? T : 1);
+        for (;; ++A) {
+            uint64_t x = A, y = T;
+            while (y) { uint64_t r = x % y; x = y; y = r; }
+            if (x == 1 || T <= 1) break;
+        }
+        const int64_t slot = tbase + (int64_t)((tl * A) % (T ? T : 1));
+        float4 lo = make_float4(fminf(xp[0], fminf(xq[0], xr[0])), fminf(xp[1], fminf(xq[1], xr[1])),
+                                fminf(xp[2], fminf(xq[2], xr[2])), __uint_as_float((uint32_t)tl));
+        float4 hi = make_float4(fmaxf(xp[0], fmaxf(xq[0], xr[0])), fmaxf(xp[1], fmaxf(xq[1], xr[1])),
+                                fmaxf(xp[2], fmaxf(xq[2], xr[2])), 0.f);
+        // a non-finite vertex gives NaN distances, which never win in the reference: push the box
+        // infinitely far away (fminf/fmaxf would silently drop the NaNs and keep a finite box)
         float chk = xp[0] + xp[1] + xp[2] + xq[0] + xq[1] + xq[2] + xr[0] + xr[1] + xr[2];
         if (!(fabsf(chk) < 3.0e38f)) {
-            float qn = __int_as_float(0x7fc00000);
-            aabb_out[2 * t] = aabb_out[2 * t + 1] = make_float4(qn, qn, qn, qn);
+            const float inf = __int_as_float(0x7f800000);
+            lo.x = lo.y = lo.z = inf;
+            hi.x = hi.y = hi.z = -inf;
         }
+        aabb_out[2 * slot] = lo;
+        aabb_out[2 * slot + 1] = hi;
     }
 
     const int dims[3] = { P.ni, P.nj, P.nk };
@@ -221,12 +265,6 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
 }
 
 // ------------------------------------------------------------------ init ----
-__device__ __forceinline__ V3 node_pos(int i, int j, int k, const g3d_tdf_params& P)
-{
-    // Vec3f gx(i*dx+origin[0], ...) (cpp:139): int -> float, one mul, one add
-    return { add(mul((float)i, P.dx), P.origin[0]), add(mul((float)j, P.dx), P.origin[1]),
-             add(mul((float)k, P.dx), P.origin[2]) };
-}
 
 // One warp per triangle walks the triangle's band box 32 nodes at a time. A node farther from the
 // triangle's bounding box than its current phi cannot win (nor tie) the `<`, so it is dropped
@@ -616,8 +654,6 @@ __global__ void unpack_occ_kernel(const uint32_t* __restrict__ bits, int64_t n_b
         out[i] = ((bits[i >> 5] >> (i & 31)) & 1u) ? 1.f : 0.f;
 }
 
-#include "g3d_tdf_exact.cuh"
-
 int grid_for(int64_t n, int block, int max_blocks)
 {
     int64_t g = (n + block - 1) / block;
@@ -705,7 +741,7 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
     prof_mark(ST_FILL, stream);
     if (total_tris > 0) {
         tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr);
+            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr);
         prof_mark(ST_PREP, stream);
         tdf_init_kernel<<<grid_for(total_tris * 32, 256, sms * 32), 256, 0, stream>>>(
             w.tri, w.box, tri_off, total_tris, p, w.key, far, cnt);
@@ -765,13 +801,30 @@ int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_
     prof_mark(ST_FILL, stream);
     if (total_tris > 0) {
         tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb);
+            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb, w.fast);
         prof_mark(ST_PREP, stream);
         constexpr int NT = exact::kNT, TILE = exact::kTile;
-        const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
-        G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        exact::tdf_exact_kernel<NT, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
-            w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
+        static int strict = -1;                     // G3D_EXACT_STRICT=1: single-stage kernel (every pair evaluated faithfully)
+        if (strict < 0) { const char* e = getenv("G3D_EXACT_STRICT"); strict = (e && atoi(e)) ? 1 : 0; }
+        if (strict) {
+            const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
+            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            exact::tdf_exact_kernel<NT, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+                w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
+        } else {
+            // filter margins of the two-stage kernel, scaled by the extent of the coordinates involved
+            float S = 0.f;
+            const int dims[3] = { p.ni, p.nj, p.nk };
+            for (int a = 0; a < 3; ++a) {
+                S = fmaxf(S, fabsf(p.origin[a]));
+                S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
+            }
+            const float eta = 2e-4f * S, kappa = 1e-6f * S * S;
+            const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4 + (size_t)(NT / 32) * 64 * 4;
+            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            exact::tdf_exact2_kernel<NT, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+                w.tri, w.fast, w.aabb, tri_off, w.parity, w.key, p, R, far, eta, kappa, nbx, nby, nbz, cnt);
+        }
         prof_mark(ST_EXACT, stream);
     }
     tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(

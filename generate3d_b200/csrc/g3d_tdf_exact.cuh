@@ -67,7 +67,8 @@ __device__ __forceinline__ float box_gap2(float4 alo, float4 ahi, V3 blo, V3 bhi
     return fmaf(gx, gx, fmaf(gy, gy, gz * gz));
 }
 
-// a NaN box (neutralised triangle) compares false and is culled; a NaN distance never wins
+// neutralised triangles carry an inverted infinite box (gap = inf): culled unless the bound is infinite,
+// in which case their NaN distances simply never win
 __device__ __forceinline__ float bound2_of(float r) { return fmaf(r * r, 1.001f, 1e-12f); }
 
 template <int NT, int TILE>
@@ -177,18 +178,20 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, d));
             const float bound2 = bound2_of(bound);
-            int q = -1;
+            uint32_t tq = 0;                         // the triangle's own index rides in lo.w of its box
             bool pass = false;
             if (l0 + lane < nlist) {
-                q = (int)s_list[l0 + lane];
-                pass = box_gap2(box[2 * q], box[2 * q + 1], brick_lo, brick_hi) <= bound2;
+                const int q = (int)s_list[l0 + lane];
+                const float4 lo = box[2 * q];
+                tq = __float_as_uint(lo.w);
+                pass = box_gap2(lo, box[2 * q + 1], brick_lo, brick_hi) <= bound2;
                 ++n_tests;
             }
             uint32_t m = __ballot_sync(0xffffffffu, pass);
             while (m) {
                 int src = __ffs(m) - 1;
                 m &= m - 1;
-                const uint32_t t = (uint32_t)(tile_base + __shfl_sync(0xffffffffu, q, src));
+                const uint32_t t = __shfl_sync(0xffffffffu, tq, src);
                 const float d = point_triangle_distance(gx, load_trirec(Tm + 4 * (int64_t)t));
                 if (d < best || (d == best && t < best_t)) { best = d; best_t = t; }
                 n_pairs += valid ? 1 : 0;
@@ -206,8 +209,256 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: two-stage evaluation. Stage 1 rates every surviving (voxel, triangle) pair with a cheap
+// squared distance that is free to use FMA (55 arithmetic instructions, no division, no square
+// root: the three clamped edge parameters use precomputed reciprocals and the saturate modifier).
+// Only pairs whose cheap distance is within a generous margin of the voxel's running cheap minimum
+// can be the minimum of the reference's float function; those few are queued and re-evaluated 32
+// at a time with the bit-faithful function (stage 2), which alone decides the result.
+//
+// Why this is still exact: let d*(t) be the faithful float distance and a(t) the cheap one, with
+// |a(t) - d*(t)| <= e for every non-flagged triangle. If t0 minimises d*, then for every t,
+// a(t) >= d*(t) - e >= d*(t0) - e >= a(t0) - 2e, so a(t0) <= min_t a(t) + 2e: t0 passes the filter
+// "a <= running min + margin" whenever margin >= 2e (the running min only decreases). The margin
+// used is 2e-4 * S absolute (S = extent of the coordinates) plus 0.1 %, about 1000x the observed
+// discrepancy. Triangles for which no such e holds -- slivers (sin^2 < 0.01), zero-length edges,
+// non-finite vertices -- are flagged at record-build time and always go to stage 2.
+struct FastRec {                                     // 5 x float4 = 80 B
+    float4 f0;   // x3.xyz, invdet (NaN = always evaluate faithfully)
+    float4 f1;   // x13.xyz, m13
+    float4 f2;   // x23.xyz, m23
+    float4 f3;   // e12.xyz, m12
+    float4 f4;   // d, 1/m13, 1/m23, 1/m12
+};
+
+__device__ __forceinline__ void store_fastrec(float4* p, V3 x1, V3 x2, V3 x3)
+{
+    const float qn = __int_as_float(0x7fc00000);
+    V3 x13 = { x1.x - x3.x, x1.y - x3.y, x1.z - x3.z }, x23 = { x2.x - x3.x, x2.y - x3.y, x2.z - x3.z };
+    V3 e12 = { x2.x - x1.x, x2.y - x1.y, x2.z - x1.z };
+    float m13 = x13.x * x13.x + x13.y * x13.y + x13.z * x13.z;
+    float m23 = x23.x * x23.x + x23.y * x23.y + x23.z * x23.z;
+    float m12 = e12.x * e12.x + e12.y * e12.y + e12.z * e12.z;
+    float d = x13.x * x23.x + x13.y * x23.y + x13.z * x23.z;
+    float det = m13 * m23 - d * d;
+    bool ok = (m13 > 0.f) && (m23 > 0.f) && (m12 > 0.f) && (det > 1e-2f * m13 * m23) && (fabsf(m13 + m23 + m12) < 1e30f) &&
+              (fabsf(x3.x) + fabsf(x3.y) + fabsf(x3.z) < 1e15f);
+    p[0] = make_float4(x3.x, x3.y, x3.z, ok ? 1.f / det : qn);
+    p[1] = make_float4(x13.x, x13.y, x13.z, m13);
+    p[2] = make_float4(x23.x, x23.y, x23.z, m23);
+    p[3] = make_float4(e12.x, e12.y, e12.z, m12);
+    p[4] = make_float4(d, 1.f / m13, 1.f / m23, 1.f / m12);
+}
+
+// cheap squared point-triangle distance; `flagged` is set for records that must go to stage 2
+__device__ __forceinline__ float fast_dist2(V3 x0, const float4* __restrict__ p, bool& flagged)
+{
+    const float4 f0 = __ldg(p), f1 = __ldg(p + 1), f2 = __ldg(p + 2), f3 = __ldg(p + 3), f4 = __ldg(p + 4);
+    flagged = !(f0.w == f0.w);
+    const float vx = x0.x - f0.x, vy = x0.y - f0.y, vz = x0.z - f0.z;
+    const float a = fmaf(f1.z, vz, fmaf(f1.y, vy, f1.x * vx));
+    const float b = fmaf(f2.z, vz, fmaf(f2.y, vy, f2.x * vx));
+    const float vv = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+    const float w23 = f0.w * fmaf(-f4.x, b, f2.w * a);
+    const float w31 = f0.w * fmaf(-f4.x, a, f1.w * b);
+    const float w12 = 1.f - w23 - w31;
+    const float plane = vv - fmaf(w31, b, w23 * a);
+    const float s1 = __saturatef(a * f4.y), s2 = __saturatef(b * f4.z);
+    const float e1 = fmaf(s1, fmaf(s1, f1.w, -2.f * a), vv);
+    const float e2 = fmaf(s2, fmaf(s2, f2.w, -2.f * b), vv);
+    const float ux = vx - f1.x, uy = vy - f1.y, uz = vz - f1.z;       // x0 - x1
+    const float c = fmaf(f3.z, uz, fmaf(f3.y, uy, f3.x * ux));
+    const float uu = fmaf(uz, uz, fmaf(uy, uy, ux * ux));
+    const float s3 = __saturatef(c * f4.w);
+    const float e3 = fmaf(s3, fmaf(s3, f3.w, -2.f * c), uu);
+    const float edge = fminf(e1, fminf(e2, e3));
+    const bool inside = (w23 >= 0.f) && (w31 >= 0.f) && (w12 >= 0.f);
+    return fmaxf(inside ? plane : edge, 0.f);
+}
+
+template <int NT, int TILE>
+__global__ void __launch_bounds__(NT, 2)
+tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fast, const float4* __restrict__ aabb,
+                  const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
+                  g3d_tdf_params P, float R, float far, float eta, float kappa, int nbx, int nby, int nbz, u64* counter)
+{
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [2][TILE * 2]
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 2 * TILE * 32);    // [TILE]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_list + TILE);             // [2]
+    int* s_count = reinterpret_cast<int*>(s_bar + 2);                         // [2]
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_count + 2);             // [NT/32][64]  t << 5 | owner lane
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t* q = s_queue + warp * 64;
+    const int nblk = nbx * nby * nbz;
+    const int mesh = blockIdx.x / nblk;
+    int b = blockIdx.x - mesh * nblk;
+    const int cbx = b % nbx; b /= nbx;
+    const int cby = b % nby, cbz = b / nby;
+    const int ni = P.ni, nj = P.nj, nk = P.nk;
+    const int64_t nvox = nvox_of(P);
+
+    const int bi0 = cbx * 8 + (warp & 1) * 4, bj0 = cby * 8 + ((warp >> 1) & 1) * 4, bk0 = cbz * 8 + (warp >> 2) * 2;
+    const int i = bi0 + (lane & 3), j = bj0 + ((lane >> 2) & 3), k = bk0 + (lane >> 4);
+    const bool valid = i < ni && j < nj && k < nk;
+    bool inside = false;
+    if (valid) {                                    // running parity along i (makelevelset3.cpp:174-182)
+        const uint32_t* par = parity + (int64_t)mesh * ((nvox + 31) / 32);
+        int64_t r0 = (int64_t)ni * (j + (int64_t)nj * k), r1 = r0 + i;
+        int cnt = 0;
+        for (int64_t w = r0 >> 5; w <= (r1 >> 5); ++w) {
+            uint32_t m = par[w];
+            if (w == (r0 >> 5)) m &= 0xffffffffu << (r0 & 31);
+            if (w == (r1 >> 5)) m &= 0xffffffffu >> (31 - (r1 & 31));
+            cnt += __popc(m);
+        }
+        inside = cnt & 1;
+    }
+    const float INF = __int_as_float(0x7f800000);
+    const V3 gx = node_pos(i, j, k, P);
+    // stage-2 state (decides the result) and stage-1 state (decides who gets a stage-2 evaluation)
+    float best = valid ? (inside ? INF : R) : 0.f;
+    uint32_t best_t = 0xffffffffu;
+    float lim2 = valid ? (inside ? INF : fmaf(R + eta, R + eta, kappa)) : -1.f;   // pass iff cheap d^2 <= lim2
+    float besta2 = lim2;
+
+    const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
+    const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
+    const V3 blk_lo = node_pos(cbx * 8, cby * 8, cbz * 8, P);
+    const V3 blk_hi = node_pos(min(cbx * 8 + 7, ni - 1), min(cby * 8 + 7, nj - 1), min(cbz * 8 + 7, nk - 1), P);
+    const int any_inside = __syncthreads_or(inside ? 1 : 0);
+    const float blk_bound2 = any_inside ? INF : fmaf(R + eta, R + eta, kappa) * 1.001f;
+
+    const int64_t t0 = tri_off[mesh];
+    const int T = (int)(tri_off[mesh + 1] - t0);
+    const float4* Tm = tri + 4 * t0;
+    const float4* Fm = fast + 5 * t0;
+    const float4* Bm = aabb + 2 * t0;
+    const int ntile = (T + TILE - 1) / TILE;
+    u64 n_pairs = 0, n_tests = 0, n_faithful = 0;
+    int qn = 0;
+
+    // stage 2 on 32 queue entries starting at `from` (entries beyond `cnt` are idle lanes)
+    auto flush = [&](int from, int cnt) {
+        __syncwarp();
+        uint32_t ent = 0;
+        float d = INF;
+        const bool have = lane < cnt;
+        if (have) {
+            ent = q[from + lane];
+            const int o = ent & 31u;
+            const V3 go = node_pos(bi0 + (o & 3), bj0 + ((o >> 2) & 3), bk0 + (o >> 4), P);
+            d = point_triangle_distance(go, load_trirec(Tm + 4 * (int64_t)(ent >> 5)));
+            ++n_faithful;
+        }
+        for (int r = 0; r < cnt; ++r) {
+            const uint32_t er = __shfl_sync(0xffffffffu, ent, r);
+            const float dr = __shfl_sync(0xffffffffu, d, r);
+            const uint32_t tr = er >> 5;
+            if ((int)(er & 31u) == lane && (dr < best || (dr == best && tr < best_t))) { best = dr; best_t = tr; }
+        }
+        __syncwarp();
+    };
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        s_count[0] = s_count[1] = 0;
+    }
+    __syncthreads();
+    if (tid == 0 && ntile > 0) {
+        uint32_t bytes = (uint32_t)min(TILE, T) * 32u;
+        mbar_expect_tx(&s_bar[0], bytes);
+        bulk_g2s(s_box, Bm, bytes, &s_bar[0]);
+    }
+    for (int it = 0; it < ntile; ++it) {
+        const int st = it & 1;
+        const int tile_base = it * TILE;
+        const int tn = min(TILE, T - tile_base);
+        if (tid == 0 && it + 1 < ntile) {
+            uint32_t bytes = (uint32_t)min(TILE, T - (tile_base + TILE)) * 32u;
+            mbar_expect_tx(&s_bar[st ^ 1], bytes);
+            bulk_g2s(s_box + (st ^ 1) * TILE * 2, Bm + 2 * (int64_t)(tile_base + TILE), bytes, &s_bar[st ^ 1]);
+        }
+        mbar_wait(&s_bar[st], (it >> 1) & 1);
+        const float4* box = s_box + st * TILE * 2;
+
+        // ---- phase A: block-level cull
+        for (int q0 = warp * 32; q0 < tn; q0 += NT) {
+            int qq = q0 + lane;
+            bool pass = false;
+            if (qq < tn) {
+                pass = box_gap2(box[2 * qq], box[2 * qq + 1], blk_lo, blk_hi) <= blk_bound2;
+                ++n_tests;
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_count[st], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)qq;
+            }
+        }
+        __syncthreads();
+        const int nlist = s_count[st];
+        if (tid == 0) s_count[st ^ 1] = 0;
+
+        // ---- phase B: brick-level cull with the running bound, stage 1 on the survivors
+        for (int l0 = 0; l0 < nlist; l0 += 32) {
+            float bound2 = lim2;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bound2 = fmaxf(bound2, __shfl_xor_sync(0xffffffffu, bound2, d));
+            bound2 *= 1.001f;
+            uint32_t tq = 0;                         // the triangle's own index rides in lo.w of its box
+            bool pass = false;
+            if (l0 + lane < nlist) {
+                const int qq = (int)s_list[l0 + lane];
+                const float4 lo = box[2 * qq];
+                tq = __float_as_uint(lo.w);
+                pass = box_gap2(lo, box[2 * qq + 1], brick_lo, brick_hi) <= bound2;
+                ++n_tests;
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, pass);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t t = __shfl_sync(0xffffffffu, tq, src);
+                bool flagged;
+                const float a2 = fast_dist2(gx, Fm + 5 * (int64_t)t, flagged);
+                n_pairs += valid ? 1 : 0;
+                const bool cand = valid && (flagged || !(a2 > lim2));
+                if (!flagged && a2 < besta2) {       // new cheap minimum: tighten the filter
+                    besta2 = a2;
+                    const float s = sqrtf(a2) * 1.001f + eta;
+                    lim2 = fmaf(s, s, kappa);
+                }
+                const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+                if (cm) {
+                    if (cand) q[qn + __popc(cm & ((1u << lane) - 1u))] = (t << 5) | (uint32_t)lane;
+                    qn += __popc(cm);
+                    if (qn >= 32) { qn -= 32; flush(qn, 32); }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (qn > 0) flush(0, qn);
+    if (valid) {
+        float phi = (best_t == 0xffffffffu) ? far : best;
+        key[(int64_t)mesh * nvox + (i + (int64_t)ni * (j + (int64_t)nj * k))] = ((u64)__float_as_uint(phi) << 32) | best_t;
+    }
+    if (counter) {
+        if (n_faithful) atomicAdd(counter + 0, n_faithful);
+        if (n_pairs) atomicAdd(counter + 2, n_pairs);
+        if (n_tests) atomicAdd(counter + 3, n_tests);
+    }
+}
+
 struct Ws {
-    float4* tri; float4* aabb; int4* box; u64* key; uint32_t* parity; size_t bytes;
+    float4* tri; float4* fast; float4* aabb; int4* box; u64* key; uint32_t* parity; size_t bytes;
 };
 
 inline Ws carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
@@ -217,6 +468,7 @@ inline Ws carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_pa
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
     int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32;
     w.tri = (float4*)take((size_t)total_tris * 64);
+    w.fast = (float4*)take((size_t)total_tris * 80);
     w.aabb = (float4*)take((size_t)total_tris * 32);
     w.box = (int4*)take((size_t)total_tris * 16);
     w.key = (u64*)take((size_t)n_mesh * nvox * 8);
