@@ -781,7 +781,8 @@ int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_
         set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
         return G3D_ERR_WORKSPACE;
     }
-    const int nbx = (p.ni + 7) / 8, nby = (p.nj + 7) / 8, nbz = (p.nk + 7) / 8;
+    constexpr int WX = exact::kWX, WY = exact::kWY, WZ = exact::kWZ, NT = WX * WY * WZ * 32, TILE = exact::kTile;
+    const int nbx = (p.ni + WX * 4 - 1) / (WX * 4), nby = (p.nj + WY * 4 - 1) / (WY * 4), nbz = (p.nk + WZ * 2 - 1) / (WZ * 2);
     const int64_t nblocks = (int64_t)n_mesh * nbx * nby * nbz;
     if (nblocks >= (int64_t)INT_MAX) { set_error("exact: too many blocks in one call (%lld)", (long long)nblocks); return G3D_ERR_INVALID; }
     const int sms = sm_count();
@@ -803,13 +804,12 @@ int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_
         tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
             verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb, w.fast);
         prof_mark(ST_PREP, stream);
-        constexpr int NT = exact::kNT, TILE = exact::kTile;
         static int strict = -1;                     // G3D_EXACT_STRICT=1: single-stage kernel (every pair evaluated faithfully)
         if (strict < 0) { const char* e = getenv("G3D_EXACT_STRICT"); strict = (e && atoi(e)) ? 1 : 0; }
         if (strict) {
             const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
-            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            exact::tdf_exact_kernel<NT, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            exact::tdf_exact_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
                 w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
         } else {
             // filter margins of the two-stage kernel, scaled by the extent of the coordinates involved
@@ -821,8 +821,8 @@ int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_
             }
             const float eta = 2e-4f * S, kappa = 1e-6f * S * S;
             const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4 + (size_t)(NT / 32) * 64 * 4;
-            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            exact::tdf_exact2_kernel<NT, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            exact::tdf_exact2_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
                 w.tri, w.fast, w.aabb, tri_off, w.parity, w.key, p, R, far, eta, kappa, nbx, nby, nbz, cnt);
         }
         prof_mark(ST_EXACT, stream);

@@ -26,8 +26,11 @@
 
 namespace exact {
 
-constexpr int kNT = 512;
-constexpr int kTile = 1024;
+// block shape in warps (each warp = a 4x4x2 brick) and triangle-box tile size. Small blocks win: the two block
+// barriers per tile cost the slowest brick's time, and a brick next to the surface does thousands of evaluations
+// while a far one does none (measured on B200, 1,024 meshes: 2x2x4 warps 105 ms, barrier stall 8.1 per issue).
+constexpr int kWX = 2, kWY = 1, kWZ = 2;
+constexpr int kTile = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,12 +74,14 @@ __device__ __forceinline__ float box_gap2(float4 alo, float4 ahi, V3 blo, V3 bhi
 // in which case their NaN distances simply never win
 __device__ __forceinline__ float bound2_of(float r) { return fmaf(r * r, 1.001f, 1e-12f); }
 
-template <int NT, int TILE>
-__global__ void __launch_bounds__(NT, 2)
+template <int WX, int WY, int WZ, int TILE>
+__global__ void __launch_bounds__(WX * WY * WZ * 32)
 tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb,
                  const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
                  g3d_tdf_params P, float R, float far, int nbx, int nby, int nbz, u64* counter)
 {
+    constexpr int NT = WX * WY * WZ * 32;
+    constexpr int BX = WX * 4, BY = WY * 4, BZ = WZ * 2;                      // nodes per block and axis
     extern __shared__ __align__(128) unsigned char s_raw[];
     float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [2][TILE * 2]
     uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 2 * TILE * 32);    // [TILE]
@@ -92,8 +97,8 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int64_t nvox = nvox_of(P);
 
-    // block = 8x8x8 nodes; warp -> 4x4x2 brick; lane -> node
-    const int bi0 = cbx * 8 + (warp & 1) * 4, bj0 = cby * 8 + ((warp >> 1) & 1) * 4, bk0 = cbz * 8 + (warp >> 2) * 2;
+    // block = BX x BY x BZ nodes; warp -> 4x4x2 brick; lane -> node
+    const int bi0 = cbx * BX + (warp % WX) * 4, bj0 = cby * BY + ((warp / WX) % WY) * 4, bk0 = cbz * BZ + (warp / (WX * WY)) * 2;
     const int i = bi0 + (lane & 3), j = bj0 + ((lane >> 2) & 3), k = bk0 + (lane >> 4);
     const bool valid = i < ni && j < nj && k < nk;
     bool inside = false;
@@ -116,8 +121,8 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
     // boxes of the brick and of the block (node positions are monotone in the index)
     const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
     const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
-    const V3 blk_lo = node_pos(cbx * 8, cby * 8, cbz * 8, P);
-    const V3 blk_hi = node_pos(min(cbx * 8 + 7, ni - 1), min(cby * 8 + 7, nj - 1), min(cbz * 8 + 7, nk - 1), P);
+    const V3 blk_lo = node_pos(cbx * BX, cby * BY, cbz * BZ, P);
+    const V3 blk_hi = node_pos(min(cbx * BX + BX - 1, ni - 1), min(cby * BY + BY - 1, nj - 1), min(cbz * BZ + BZ - 1, nk - 1), P);
     const int any_inside = __syncthreads_or(inside ? 1 : 0);
     const float blk_bound2 = any_inside ? __int_as_float(0x7f800000) : bound2_of(R);
 
@@ -222,7 +227,7 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
 // a(t) >= d*(t) - e >= d*(t0) - e >= a(t0) - 2e, so a(t0) <= min_t a(t) + 2e: t0 passes the filter
 // "a <= running min + margin" whenever margin >= 2e (the running min only decreases). The margin
 // used is 2e-4 * S absolute (S = extent of the coordinates) plus 0.1 %, about 1000x the observed
-// discrepancy. Triangles for which no such e holds -- slivers (sin^2 < 0.01), zero-length edges,
+// discrepancy. Triangles for which no such e holds -- slivers (sin^2 < 0.001, where the cheap rating could be off by more than ~6e-5 relative), zero-length edges,
 // non-finite vertices -- are flagged at record-build time and always go to stage 2.
 struct FastRec {                                     // 5 x float4 = 80 B
     float4 f0;   // x3.xyz, invdet (NaN = always evaluate faithfully)
@@ -242,7 +247,7 @@ __device__ __forceinline__ void store_fastrec(float4* p, V3 x1, V3 x2, V3 x3)
     float m12 = e12.x * e12.x + e12.y * e12.y + e12.z * e12.z;
     float d = x13.x * x23.x + x13.y * x23.y + x13.z * x23.z;
     float det = m13 * m23 - d * d;
-    bool ok = (m13 > 0.f) && (m23 > 0.f) && (m12 > 0.f) && (det > 1e-2f * m13 * m23) && (fabsf(m13 + m23 + m12) < 1e30f) &&
+    bool ok = (m13 > 0.f) && (m23 > 0.f) && (m12 > 0.f) && (det > 1e-3f * m13 * m23) && (fabsf(m13 + m23 + m12) < 1e30f) &&
               (fabsf(x3.x) + fabsf(x3.y) + fabsf(x3.z) < 1e15f);
     p[0] = make_float4(x3.x, x3.y, x3.z, ok ? 1.f / det : qn);
     p[1] = make_float4(x13.x, x13.y, x13.z, m13);
@@ -277,12 +282,14 @@ __device__ __forceinline__ float fast_dist2(V3 x0, const float4* __restrict__ p,
     return fmaxf(inside ? plane : edge, 0.f);
 }
 
-template <int NT, int TILE>
-__global__ void __launch_bounds__(NT, 2)
+template <int WX, int WY, int WZ, int TILE>
+__global__ void __launch_bounds__(WX * WY * WZ * 32)
 tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fast, const float4* __restrict__ aabb,
                   const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
                   g3d_tdf_params P, float R, float far, float eta, float kappa, int nbx, int nby, int nbz, u64* counter)
 {
+    constexpr int NT = WX * WY * WZ * 32;
+    constexpr int BX = WX * 4, BY = WY * 4, BZ = WZ * 2;                      // nodes per block and axis
     extern __shared__ __align__(128) unsigned char s_raw[];
     float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [2][TILE * 2]
     uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 2 * TILE * 32);    // [TILE]
@@ -300,7 +307,7 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int64_t nvox = nvox_of(P);
 
-    const int bi0 = cbx * 8 + (warp & 1) * 4, bj0 = cby * 8 + ((warp >> 1) & 1) * 4, bk0 = cbz * 8 + (warp >> 2) * 2;
+    const int bi0 = cbx * BX + (warp % WX) * 4, bj0 = cby * BY + ((warp / WX) % WY) * 4, bk0 = cbz * BZ + (warp / (WX * WY)) * 2;
     const int i = bi0 + (lane & 3), j = bj0 + ((lane >> 2) & 3), k = bk0 + (lane >> 4);
     const bool valid = i < ni && j < nj && k < nk;
     bool inside = false;
@@ -326,8 +333,8 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
 
     const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
     const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
-    const V3 blk_lo = node_pos(cbx * 8, cby * 8, cbz * 8, P);
-    const V3 blk_hi = node_pos(min(cbx * 8 + 7, ni - 1), min(cby * 8 + 7, nj - 1), min(cbz * 8 + 7, nk - 1), P);
+    const V3 blk_lo = node_pos(cbx * BX, cby * BY, cbz * BZ, P);
+    const V3 blk_hi = node_pos(min(cbx * BX + BX - 1, ni - 1), min(cby * BY + BY - 1, nj - 1), min(cbz * BZ + BZ - 1, nk - 1), P);
     const int any_inside = __syncthreads_or(inside ? 1 : 0);
     const float blk_bound2 = any_inside ? INF : fmaf(R + eta, R + eta, kappa) * 1.001f;
 
