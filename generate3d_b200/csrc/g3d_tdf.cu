@@ -424,7 +424,17 @@ __device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
     dk = (q8 == 0 || q8 == 3 || q8 == 4 || q8 == 7) ? 1 : -1;
 }
 
-template <int NT>
+// CL = true: one mesh per thread-block CLUSTER (large grids, small batches): the CTAs of a cluster split every
+// level between them and meet at a hardware cluster barrier, whose release/acquire also orders the global-memory
+// keys between the SMs involved.
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+
+template <int NT, bool CL>
 __global__ void __launch_bounds__(NT)
 tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                  const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
@@ -452,7 +462,8 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
         s_prev[s][r] = thr;                         // examine nb iff chg[nb] > thr
     }
     __syncthreads();
-    const int mesh = blockIdx.x;
+    const int csize = CL ? (int)cluster_nctarank() : 1, crank = CL ? (int)cluster_ctarank() : 0;
+    const int mesh = blockIdx.x / csize;
     const int64_t nvox = nvox_of(P);
     u64* K = key + (int64_t)mesh * nvox;
     uint8_t* G = chg + (int64_t)mesh * nvox;
@@ -469,7 +480,7 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
                   t5 = s_prev[s][5], t6 = s_prev[s][6];
         for (int L = 0; L < nlev; ++L) {
             const int beg = s_lev[L], end = s_lev[L + 1];
-            for (int qb = beg + warp * 32; qb < end; qb += NT) {
+            for (int qb = beg + crank * NT + warp * 32; qb < end; qb += NT * csize) {
                 const int q = qb + lane;
                 int c0 = -1, c1 = -1, c2 = -1, c3 = -1, c4 = -1, c5 = -1, c6 = -1, ct = -1, n = 0;
                 uint32_t need = 0, pos = 0;
@@ -565,7 +576,7 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
                     }
                 }
             }
-            __syncthreads();
+            if (CL) cluster_barrier(); else __syncthreads();
         }
     }
     if (counter && n_eval) atomicAdd(counter + 1, n_eval);
@@ -665,14 +676,28 @@ int grid_for(int64_t n, int block, int max_blocks)
 }  // namespace
 
 namespace {
-template <int NT>
-int launch_sweep_nt(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
-                    cudaStream_t stream)
+template <int NT, bool CL>
+int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p,
+                    u64* cnt, cudaStream_t stream)
 {
     const int lev_words = (nlev + 1 + 3) & ~3;
     const size_t smem = (size_t)(lev_words + (NT / 32) * 3 * kSweepQueue) * 4;
-    G3D_CUDA_TRY(cudaFuncSetAttribute(tdf_sweep_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tdf_sweep_kernel<NT><<<n_mesh, NT, smem, stream>>>(w.key, w.chg, w.tri, tri_off, w.order, w.level_start, nlev, lev_words, p, cnt);
+    auto kern = tdf_sweep_kernel<NT, CL>;
+    G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_mesh * csize));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL ? 1 : 0;
+    G3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, w.key, w.chg, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
+                                    (const int32_t*)w.level_start, nlev, lev_words, p, cnt));
     return G3D_OK;
 }
 
@@ -682,15 +707,29 @@ int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, c
     // Threads per mesh. Small CTAs win for 32^3-class grids (measured on B200, 1,024 meshes: 128 thr 22.2 ms,
     // 256 thr 24.4, 512 thr 28.4, 1024 thr 31.1): more meshes are resident per SM, so one mesh's barrier
     // wait is covered by another mesh's arithmetic. Large grids get more threads per mesh.
-    static int forced = -1;
+    static int forced = -1, forced_cl = -1;
     if (forced < 0) { const char* e = getenv("G3D_SWEEP_THREADS"); forced = e ? atoi(e) : 0; }
+    if (forced_cl < 0) { const char* e = getenv("G3D_SWEEP_CLUSTER"); forced_cl = e ? atoi(e) : 0; }
     int64_t widest = (int64_t)(p.ni - 1) * (p.nj - 1);           // upper bound on a level's node count
-    int nt = forced ? forced : (widest >= 16384 ? 1024 : (widest >= 4096 ? 512 : (widest >= 2048 ? 256 : 128)));
+    int nt = widest >= 16384 ? 1024 : (widest >= 4096 ? 512 : (widest >= 2048 ? 256 : 128));
+    // a batch too small to fill the GPU with small CTAs is latency-bound per mesh: give each mesh more threads,
+    // and a whole cluster of CTAs when one CTA cannot cover a level
+    const int sms = sm_count();
+    int csize = 1;
+    if (n_mesh < sms) nt = 1024;
+    else if (n_mesh < 2 * sms) nt = nt < 512 ? 512 : nt;
+    else if (n_mesh < 4 * sms) nt = nt < 256 ? 256 : nt;
+    if (nt == 1024 && widest > 2048) {
+        while (csize < 8 && (int64_t)csize * 1024 < widest / 2 && (int64_t)n_mesh * csize * 2 <= sms) csize *= 2;
+    }
+    if (forced) nt = forced;
+    if (forced_cl) { csize = forced_cl; nt = 1024; }
+    if (csize > 1) return launch_sweep_nt<1024, true>(n_mesh, csize, nlev, w, tri_off, p, cnt, stream);
     switch (nt) {
-        case 128: return launch_sweep_nt<128>(n_mesh, nlev, w, tri_off, p, cnt, stream);
-        case 512: return launch_sweep_nt<512>(n_mesh, nlev, w, tri_off, p, cnt, stream);
-        case 1024: return launch_sweep_nt<1024>(n_mesh, nlev, w, tri_off, p, cnt, stream);
-        default: return launch_sweep_nt<256>(n_mesh, nlev, w, tri_off, p, cnt, stream);
+        case 128: return launch_sweep_nt<128, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
+        case 512: return launch_sweep_nt<512, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
+        case 1024: return launch_sweep_nt<1024, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
+        default: return launch_sweep_nt<256, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
     }
 }
 }  // namespace
