@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
 UNITS = {
     "g3d_tdf.cu": ["-fmad=false"],
     "g3d_raycast.cu": ["-fmad=false"],
+    "g3d_next.cu": ["-fmad=false"],
     "g3d_capi.cu": [],
     "g3d_mesh_io.cpp": [],
 }

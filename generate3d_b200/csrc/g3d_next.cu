@@ -1,0 +1,176 @@
+// g3d_next.cu -- the first two "next" rows of the scope table:
+//   occ_to_df      occupancy -> 26-neighbour chamfer distance field (Network/data_utils.py:115-168,
+//                  occ_to_df.py:16-62), used for the occ_df_gt tensor and inside validation;
+//   raycast colour per-voxel mean colour of the valid-depth pixels of the voxel's box (raytracing.py:85-120).
+#include "g3d_internal.h"
+
+namespace g3d {
+
+namespace {
+
+// ------------------------------------------------------------------------------- occ_to_df ----
+// What the reference computes, once its aliasing is taken into account (`df = new_df` makes both names
+// one tensor, so the allclose loop ends after its first trip): a (dim+2)^3 grid, 0 at occupied cells and
+// inf elsewhere, relaxed with the 27-offset Euclidean kernel exactly TWICE -- or not at all when the first
+// relaxation moves no cell from inf to finite (empty or full grids), because then the loop is never entered
+// and the untouched initial field is returned. Values above trunc become `over`.
+// After one relaxation a cell can only hold 0, 1, sqrt2, sqrt3 or inf, so the intermediate grid is kept as
+// one byte per cell in shared memory.
+__global__ void __launch_bounds__(512)
+occ_to_df_kernel(const float* __restrict__ occ, int dim, int pred, float trunc, float over, float* __restrict__ out)
+{
+    extern __shared__ uint8_t s_grid[];             // [2][(dim+2)^3] codes: 0 -> 0, 1 -> 1, 2 -> sqrt2, 3 -> sqrt3, 4 -> inf
+    const int n = dim + 2, n2 = n * n, n3 = n2 * n, d3 = dim * dim * dim;
+    uint8_t* c0 = s_grid;
+    uint8_t* c1 = s_grid + n3;
+    const float* in = occ + (size_t)blockIdx.x * d3;
+    float* o = out + (size_t)blockIdx.x * d3;
+    const float sq2 = sqrtf(2.f), sq3 = sqrtf(3.f), inf = __int_as_float(0x7f800000);
+    for (int q = threadIdx.x; q < n3; q += blockDim.x) { c0[q] = 4; c1[q] = 4; }
+    __syncthreads();
+    for (int q = threadIdx.x; q < d3; q += blockDim.x) {
+        const int x = q % dim, y = (q / dim) % dim, z = q / (dim * dim);
+        const float v = in[q];
+        bool on;
+        if (pred) on = (1.f / (1.f + expf(-v))) >= 0.5f;            // preprocess_occ: sigmoid >= 0.5
+        else on = (v == 1.f);
+        if (on) c0[(z + 1) * n2 + (y + 1) * n + (x + 1)] = 0;
+    }
+    __syncthreads();
+    int moved = 0;
+    for (int q = threadIdx.x; q < d3; q += blockDim.x) {
+        const int x = q % dim, y = (q / dim) % dim, z = q / (dim * dim);
+        const int c = (z + 1) * n2 + (y + 1) * n + (x + 1);
+        int best = 4;
+        if (c0[c] == 0) best = 0;
+        else {
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int k = (dz != 0) + (dy != 0) + (dx != 0);   // 1, 2, 3 -> 1, sqrt2, sqrt3
+                        if (k && c0[c + dz * n2 + dy * n + dx] == 0) best = min(best, k);
+                    }
+            if (best < 4) moved = 1;
+        }
+        c1[c] = (uint8_t)best;
+    }
+    const int any_moved = __syncthreads_or(moved);
+    const float val[5] = { 0.f, 1.f, sq2, sq3, inf };
+    const float ker[4] = { 0.f, 1.f, sq2, sq3 };
+    for (int q = threadIdx.x; q < d3; q += blockDim.x) {
+        const int x = q % dim, y = (q / dim) % dim, z = q / (dim * dim);
+        const int c = (z + 1) * n2 + (y + 1) * n + (x + 1);
+        float best;
+        if (!any_moved) best = c0[c] == 0 ? 0.f : inf;
+        else {
+            best = inf;
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int k = (dz != 0) + (dy != 0) + (dx != 0);
+                        best = fminf(best, __fadd_rn(val[c1[c + dz * n2 + dy * n + dx]], ker[k]));
+                    }
+        }
+        o[q] = best > trunc ? over : best;
+    }
+}
+
+// ---------------------------------------------------------------------------- colour raycast ----
+__device__ __forceinline__ int round_clamp_px(float p, int cmax)
+{
+    float r = rintf(p);
+    if (!(fabsf(r) < 9.2e18f)) return 0;
+    if (r <= 0.f) return 0;
+    if (r >= (float)cmax) return cmax;
+    return (int)r;
+}
+
+__global__ void __launch_bounds__(256)
+raycast_color_kernel(const uint8_t* __restrict__ depth, const uint8_t* __restrict__ color, const float* __restrict__ pose,
+                     int H, int W, float focal, float cx, float cy, int clamp_max, int dim, float inv_dim,
+                     uint16_t* __restrict__ out)
+{
+    const int view = blockIdx.y;
+    const int d2 = dim * dim, d3 = d2 * dim;
+    const int lin = blockIdx.x * blockDim.x + threadIdx.x;              // z*dim^2 + y*dim + x (raytracing.py:44-51)
+    if (lin >= d3) return;
+    const int x = lin % dim, y = (lin / dim) % dim, z = lin / d2;
+    const float* P = pose + (size_t)view * 16;
+    int umin = 1 << 30, vmin = 1 << 30, umax = -1, vmax = -1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float wx = __fadd_rn(__fmul_rn(inv_dim, (float)(x + (k & 1))), -0.5f);
+        const float wy = __fadd_rn(__fmul_rn(inv_dim, (float)(y + ((k >> 1) & 1))), -0.5f);
+        const float wz = __fadd_rn(__fmul_rn(inv_dim, (float)(z + (k >> 2))), -0.5f);
+        const float camx = fmaf(P[3], 1.f, fmaf(P[2], wz, fmaf(P[1], wy, __fmul_rn(P[0], wx))));
+        const float camy = fmaf(P[7], 1.f, fmaf(P[6], wz, fmaf(P[5], wy, __fmul_rn(P[4], wx))));
+        const float camz = fmaf(P[11], 1.f, fmaf(P[10], wz, fmaf(P[9], wy, __fmul_rn(P[8], wx))));
+        const float az = fabsf(camz);
+        const int u = round_clamp_px(__fadd_rn(__fdiv_rn(__fmul_rn(camx, focal), az), cx), clamp_max);
+        const int v = round_clamp_px(__fadd_rn(__fdiv_rn(__fmul_rn(-camy, focal), az), cy), clamp_max);
+        umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
+    }
+    const int u0 = min(umin, W), u1 = min(umax, W), v0 = min(vmin, H), v1 = min(vmax, H);
+    const uint8_t* D = depth + (size_t)view * H * W;
+    const uint8_t* C = color + (size_t)view * H * W * 3;
+    unsigned sr = 0, sg = 0, sb = 0, cnt = 0;
+    for (int v = v0; v < v1; ++v)
+        for (int u = u0; u < u1; ++u)
+            if (D[(size_t)v * W + u] > 0) {                             // raytracing.py:104-105
+                const uint8_t* c = C + ((size_t)v * W + u) * 3;
+                sr += c[0]; sg += c[1]; sb += c[2]; ++cnt;
+            }
+    // torch.mean of <= a few hundred byte values: the sum is exact in float, the mean is sum / count;
+    // then ceil and uint16 (raytracing.py:107-111); 256 marks "no valid pixel" (:96)
+    uint16_t r = 256, g = 256, b = 256;
+    if (cnt) {
+        r = (uint16_t)ceilf(__fdiv_rn((float)sr, (float)cnt));
+        g = (uint16_t)ceilf(__fdiv_rn((float)sg, (float)cnt));
+        b = (uint16_t)ceilf(__fdiv_rn((float)sb, (float)cnt));
+    }
+    uint16_t* o = out + ((size_t)view * d3 + ((size_t)x * dim + y) * dim + z) * 3;   // [x][y][z][rgb] (:111)
+    o[0] = r; o[1] = g; o[2] = b;
+}
+
+}  // namespace
+
+}  // namespace g3d
+
+using namespace g3d;
+
+extern "C" int g3d_occ_to_df_batch(const float* occ, int32_t n, int32_t dim, int32_t pred, float trunc, float over,
+                                   float* out, void* cuda_stream)
+{
+    if (n < 0 || dim < 1 || dim > 56) { set_error("occ_to_df: bad n/dim (dim <= 56)"); return G3D_ERR_INVALID; }
+    if (n == 0) return G3D_OK;
+    if (!occ || !out) { set_error("occ_to_df: NULL pointer"); return G3D_ERR_INVALID; }
+    const size_t smem = (size_t)2 * (dim + 2) * (dim + 2) * (dim + 2);
+    G3D_CUDA_TRY(cudaFuncSetAttribute(occ_to_df_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    occ_to_df_kernel<<<(unsigned)n, 512, smem, (cudaStream_t)cuda_stream>>>(occ, dim, pred, trunc, over, out);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+extern "C" int g3d_raycast_color_batch(const uint8_t* depth, const uint8_t* color, const float* pose, int32_t n_view,
+                                       int32_t H, int32_t W, float focal, float cx, float cy, int32_t clamp_max,
+                                       int32_t dim, uint16_t* out, void* cuda_stream)
+{
+    if (n_view < 0 || H < 1 || W < 1 || dim < 1 || dim > 1023 || clamp_max < 0 || n_view > 65535) {
+        set_error("raycast_color: bad arguments");
+        return G3D_ERR_INVALID;
+    }
+    if (n_view == 0) return G3D_OK;
+    if (!depth || !color || !pose || !out) { set_error("raycast_color: NULL pointer"); return G3D_ERR_INVALID; }
+    const int d3 = dim * dim * dim;
+    dim3 grid((unsigned)((d3 + 255) / 256), (unsigned)n_view);
+    raycast_color_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(depth, color, pose, H, W, focal, cx, cy, clamp_max,
+                                                                      dim, 1.0f / (float)dim, out);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}

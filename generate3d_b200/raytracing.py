@@ -98,6 +98,42 @@ def occ_rows(occ_zyx, color=(169, 0, 255)):
     return "".join("%d %d %d %d %d %d\n" % (i, j, k, *color) for i, j, k in zip(x, y, z))
 
 
+def raycast_color_batch(depth, color, poses, dim=None, focal=None, cx=None, cy=None, clamp_max=None, device=None):
+    """Colour raycast for a batch: depth u8 [V,H,W], color u8 [V,H,W,3], poses f32 [V,4,4] ->
+    int16 [V, dim, dim, dim, 3] in [x][y][z][rgb] order, 256 = no valid pixel (raytracing.py:85-120)."""
+    device = _device(device)
+    with torch.cuda.device(device):
+        dim = config.vox_dim if dim is None else dim
+        poses = _to_dev(poses, torch.float32, device).reshape(-1, 16)
+        depth = _to_dev(depth, torch.uint8, device)
+        color = _to_dev(color, torch.uint8, device)
+        V, H, W = poses.shape[0], int(depth.shape[-2]), int(depth.shape[-1])
+        focal = config.focal if focal is None else focal
+        cx = W / 2 if cx is None else cx
+        cy = H / 2 if cy is None else cy
+        clamp_max = config.index_clamp_max if clamp_max is None else clamp_max
+        out = torch.empty((V, dim, dim, dim, 3), dtype=torch.int16, device=device)
+        _lib.check(_lib.lib().g3d_raycast_color_batch(depth.data_ptr(), color.data_ptr(), poses.data_ptr(), V, H, W,
+                                                      focal, cx, cy, clamp_max, dim, out.data_ptr(),
+                                                      torch.cuda.current_stream(device).cuda_stream))
+        return out
+
+
+def raycast(txt_file, pose_file, color_file, depth_file):
+    """raytracing.py:85-120 (the colour variant raytracing_color.py enables): rows 'x y z r g b' for every voxel
+    that saw at least one valid-depth pixel."""
+    from PIL import Image
+    color = torch.from_numpy(np.array(Image.open(color_file))[..., :3].copy())
+    depth = torch.from_numpy(np.array(Image.open(depth_file)))
+    pose = load_pose(pose_file)
+    g = raycast_color_batch(depth.to(torch.uint8).unsqueeze(0), color.unsqueeze(0), pose.unsqueeze(0),
+                            cx=config.render_img_width / 2, cy=config.render_img_height / 2)[0].cpu().numpy()
+    pos = np.argwhere(np.all(g < 256, axis=3))
+    with open(txt_file, "w") as f:
+        for i, j, k in pos:
+            f.write("%d %d %d %d %d %d\n" % (i, j, k, g[i, j, k, 0], g[i, j, k, 1], g[i, j, k, 2]))
+
+
 def raycast_depth(txt_file, pose_file, depth_file):
     """raytracing.py:122-144: depth PNG + pose JSON -> occupancy txt."""
     from PIL import Image

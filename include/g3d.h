@@ -170,6 +170,24 @@ int g3d_write_df(const char* path, const int32_t* dims3, float res, const float*
 int g3d_read_df(const char* path, int32_t* dims3, float* res, float* grid2world16, float* sdf,
                 int64_t capacity);
 
+/* ---------------------------------------------------- "next" rows ----
+ * occ_to_df (Network/data_utils.py:115-168; occ_to_df.py:16-62): occupancy -> 26-neighbour chamfer
+ * distance field, for a batch. occ f32 [n, dim, dim, dim] in [z][y][x] order; pred != 0: a cell is
+ * occupied when sigmoid(x) >= 0.5 (preprocess_occ, data_utils.py:100-112), else when x == 1. The reference
+ * relaxes the field exactly twice (its convergence loop ends after one trip because `df = new_df`
+ * aliases the tensors), or not at all for a grid in which no free cell touches an occupied one.
+ * Values above trunc become `over` (trunc in data_utils.py:164-165, trunc + 1 in occ_to_df.py:59-60).
+ * out f32 [n, dim, dim, dim], same order. Device pointers. */
+int g3d_occ_to_df_batch(const float* occ, int32_t n, int32_t dim, int32_t pred, float trunc, float over,
+                        float* out, void* cuda_stream);
+
+/* Colour raycast (raytracing.py:85-120): per voxel the mean colour of the pixels of its box whose depth
+ * is > 0, ceil'ed; 256 = no such pixel. color u8 [n_view, H, W, 3]; out u16 [n_view, dim, dim, dim, 3]
+ * in [x][y][z][rgb] order (the order in which the reference's txt rows are indexed). Device pointers. */
+int g3d_raycast_color_batch(const uint8_t* depth, const uint8_t* color, const float* pose, int32_t n_view,
+                            int32_t H, int32_t W, float focal, float cx, float cy, int32_t clamp_max,
+                            int32_t dim, uint16_t* out, void* cuda_stream);
+
 /* ------------------------------------------------------------ profiling ----
  * Off by default. flags bit 0: record a CUDA event on the caller's stream between the kernels
  * of each g3d_tdf_batch / g3d_raycast_batch call (bench.py's per-kernel timing);

@@ -1,0 +1,67 @@
+"""occupancy -> chamfer DF and the colour raycast, vs the reference's own outputs
+(tests/golden/occ_df.npz, raycast_color.npz from make_golden_next.py) and the numpy restatements."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from generate3d_b200 import synthetic as S
+
+
+def test_occ_to_df_oracle_vs_reference(oracle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "occ_df.npz"))
+    for q in range(z["occ"].shape[0]):
+        want = z["df_false"][q][0]                                            # [z][y][x]
+        assert np.array_equal(oracle.occ_to_df(z["occ"][q], 3.0).view(np.uint32), want.view(np.uint32)), q
+        occ_pred = (1.0 / (1.0 + np.exp(-z["logits"][q].astype(np.float32))) >= 0.5).astype(np.uint8)
+        assert np.array_equal(oracle.occ_to_df(occ_pred, 3.0), z["df_true"][q][0]), q
+        xyz = np.transpose(z["occ"][q], (2, 1, 0))
+        assert np.array_equal(oracle.occ_to_df(xyz, 3.0, over=4.0), z["df_script"][q]), q
+
+
+def test_raycast_color_oracle_vs_reference(oracle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "raycast_color.npz"))
+    for q in range(z["pose"].shape[0]):
+        got = oracle.raycast_color(z["depth"][q], z["color"][q], z["pose"][q])
+        assert np.array_equal(got, z["grid_xyz"][q]), q
+
+
+@pytest.mark.gpu
+def test_occ_to_df_gpu_vs_reference(g3d, oracle, golden_dir):
+    from generate3d_b200 import data_utils
+    z = np.load(os.path.join(golden_dir, "occ_df.npz"))
+    occ = torch.from_numpy(z["occ"].astype(np.float32)).cuda().unsqueeze(1)  # [B,1,D,H,W]
+    dfs = data_utils.occs_to_dfs(occ, 3.0, pred=False)
+    assert tuple(dfs.shape) == (occ.shape[0], 1, 32, 32, 32)
+    assert np.array_equal(dfs.cpu().numpy().view(np.uint32), z["df_false"].view(np.uint32))
+    one = data_utils.occ_to_df(occ[0], 3.0, pred=False)
+    assert np.array_equal(one.cpu().numpy(), z["df_false"][0])
+    lg = torch.from_numpy(z["logits"]).cuda().unsqueeze(1)
+    assert np.array_equal(data_utils.occs_to_dfs(lg, 3.0, pred=True).cpu().numpy(), z["df_true"])
+    for q in (0, 4):
+        xyz = torch.from_numpy(np.transpose(z["occ"][q], (2, 1, 0)).astype(np.float32).copy()).cuda()
+        assert np.array_equal(data_utils.occ_to_df_xyz(xyz, 3.0).cpu().numpy(), z["df_script"][q])
+    # other sizes against the restatement
+    rng = np.random.default_rng(5)
+    for dim in (8, 20, 40):
+        g = (rng.uniform(size=(3, dim, dim, dim)) < 0.01).astype(np.float32)
+        got = data_utils.occs_to_dfs(torch.from_numpy(g).cuda().unsqueeze(1), 2.5, pred=False).cpu().numpy()
+        for q in range(3):
+            assert np.array_equal(got[q, 0], oracle.occ_to_df(g[q], 2.5)), (dim, q)
+
+
+@pytest.mark.gpu
+def test_raycast_color_gpu_vs_reference(g3d, oracle, golden_dir, tmp_path):
+    from PIL import Image
+    from generate3d_b200 import raytracing
+    z = np.load(os.path.join(golden_dir, "raycast_color.npz"))
+    g = raytracing.raycast_color_batch(z["depth"], z["color"], z["pose"])
+    assert np.array_equal(g.cpu().numpy().astype(np.uint16), z["grid_xyz"])
+    Image.fromarray(z["depth"][0], mode="L").save(tmp_path / "d.png")
+    Image.fromarray(z["color"][0], mode="RGB").save(tmp_path / "c.png")
+    with open(tmp_path / "p.json", "w") as f:
+        json.dump({"pose": S.pose_json_payload(0)}, f)
+    raytracing.raycast(str(tmp_path / "o.txt"), str(tmp_path / "p.json"), str(tmp_path / "c.png"), str(tmp_path / "d.png"))
+    assert (tmp_path / "o.txt").read_bytes() == bytes(z["first_txt"])
