@@ -52,6 +52,14 @@ def parse():
     return ap.parse_args()
 
 
+def traffic_table():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -258,6 +266,10 @@ def run_b200(args, rank, world, local):
         "note": "faithful arithmetic issues no FMA (bit parity with the CPU reference), so 0.5 of the FMA peak is its ceiling",
         "traffic": None,
     }
+    tt = traffic_table().get(roofline["kernel"])
+    if tt and M == 1024 and args.n == 18:
+        roofline["traffic"] = tt["bytes_per_launch"]
+        roofline["traffic_source"] = tt["source"] + " (ncu --set full, same workload)"
 
     # ---- the other TDF mode, same batch, fewer steps: rides along under "other_mode"
     other = "exact" if args.mode == "faithful" else "faithful"
@@ -329,7 +341,8 @@ def run_b200(args, rank, world, local):
                     "value": world * nview_b * 256 * 256 / (msb * 1e-3), "ms_per_step": msb},
         "roofline": {"kernel": "raycast_kernel", "bound": "hbm", "achieved": ray_bw, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": ray_bw / peaks["hbm_gbs"], "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs",
-                     "bytes_per_view": bytes_per_view, "traffic": None},
+                     "bytes_per_view": bytes_per_view,
+                     "traffic": (traffic_table().get("raycast_kernel", {}).get("bytes_per_view", 0) * nview_b) or None},
     }
     ray_launches = max(args.steps, 20) + args.steps
 

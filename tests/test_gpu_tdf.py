@@ -252,3 +252,38 @@ def test_exact_mode_untruncated_and_ragged(g3d, oracle):
         assert np.array_equal(_bits(np.abs(r["sdf"][m].cpu().numpy())), _bits(bf * np.float32(16))), m
         if m != 2:
             assert np.array_equal(r["closest_tri"][m].cpu().numpy(), bt), m
+
+
+def test_cadvoxelization_dropin_writes_reference_files(g3d, oracle, tmp_path):
+    """The batched CADVoxelization mirror leaves the same two files per model the reference pipeline does."""
+    from generate3d_b200 import CADVoxelization as CV
+    root = tmp_path / "shapenet"
+    want = {}
+    for k in range(5):
+        v, t = S.table_mesh(3, 60 + k, scale=0.9)
+        d = root / "04379243" / ("model%02d" % k) / "models"
+        d.mkdir(parents=True)
+        with open(d / "model_normalized.obj", "w") as f:
+            for p in v:
+                f.write("v %.9g %.9g %.9g\n" % tuple(p))
+            for tri in t:
+                f.write("f %d %d %d\n" % tuple(tri + 1))
+        want["model%02d" % k] = oracle.dfgen(t, v, 32)
+    bad = root / "04379243" / "broken" / "models"
+    bad.mkdir(parents=True)
+    (bad / "model_normalized.obj").write_text("# nothing here\n")
+    params = {"shapenet": str(root), "shapenet_voxelized": str(tmp_path / "vox") + "/"}
+    models = CV.list_models(params)
+    assert len(models) == 6
+    keep = {}
+    done, failed = CV.voxelize_models(models, params["shapenet_voxelized"], chunk=4, keep=keep)
+    assert done == 5 and [f[0] for f in failed] == ["broken"]
+    for mid, g in want.items():
+        ref = tmp_path / "ref.df"
+        oracle.write_df(str(ref), g["sdf"], g["grid2world"])
+        out = tmp_path / "vox" / "04379243" / (mid + "__0__.df")
+        assert out.read_bytes() == ref.read_bytes()
+        assert (tmp_path / "vox" / "04379243" / (mid + "__0__.txt")).read_text() == oracle.gt_occ_txt_rows(g["sdf"])
+        assert keep[mid]["tdf"].is_cuda
+    done2, _ = CV.voxelize_models(models, params["shapenet_voxelized"], chunk=4)      # resume: nothing left but the broken one
+    assert done2 == 0
