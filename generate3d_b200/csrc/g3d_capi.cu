@@ -41,10 +41,9 @@ int sm_count()
 
 struct Prof {
     int flags = 0;
-    cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t ev[kProfMarks] = {};
     bool have_events = false;
-    bool marked[ST_COUNT + 1] = {};
-    int order[ST_COUNT + 1] = {};                   // stage recorded at slot i (slot 0 = begin)
+    int order[kProfMarks] = {};                     // stage recorded at slot i (slot 0 = begin)
     int n_marks = 0;
     unsigned long long* counters = nullptr;
 };
@@ -67,7 +66,7 @@ void prof_begin(cudaStream_t s)
 void prof_mark(int stage, cudaStream_t s)
 {
     Prof& p = g_prof;
-    if (!(p.flags & G3D_PROF_EVENTS) || p.n_marks == 0 || p.n_marks > ST_COUNT) return;
+    if (!(p.flags & G3D_PROF_EVENTS) || p.n_marks == 0 || p.n_marks >= kProfMarks) return;
     cudaEventRecord(p.ev[p.n_marks], s);
     p.order[p.n_marks] = stage;
     ++p.n_marks;
@@ -92,9 +91,13 @@ static __global__ void fp32_probe_kernel(float* out, int iters)
     if (r == 123.456f) out[0] = r;                  // keeps the chain alive, never true in practice
 }
 
+constexpr int kHostChunks = 4;
+
 struct g3d_context {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                  // kernels and device->host copies
+    cudaStream_t s_in = nullptr;                    // host->device copies of the host-buffer front end
+    cudaEvent_t ev_in[kHostChunks] = {};
     char* arena = nullptr;
     size_t arena_bytes = 0;
 };
@@ -147,8 +150,7 @@ size_t g3d_tdf_workspace_bytes(int32_t n_mesh, int64_t total_verts, int64_t tota
 {
     (void)total_verts;
     if (!params || n_mesh < 0 || total_tris < 0) return 0;
-    return params->mode == G3D_MODE_EXACT ? tdf_exact_workspace_bytes(n_mesh, total_tris, *params)
-                                          : tdf_faithful_workspace_bytes(n_mesh, total_tris, *params);
+    return tdf_workspace_bytes(n_mesh, total_tris, *params);
 }
 
 int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_verts, const uint32_t* tris,
@@ -159,14 +161,11 @@ int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_ver
     if (n_mesh > 0 && (!vert_off || !tri_off)) { set_error("tdf: offsets are NULL"); return G3D_ERR_INVALID; }
     if ((total_verts > 0 && !verts) || (total_tris > 0 && !tris)) { set_error("tdf: verts/tris are NULL"); return G3D_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    if (params->mode == G3D_MODE_FAITHFUL)
-        return tdf_faithful_launch(verts, vert_off, total_verts, tris, tri_off, total_tris, n_mesh, *params, *out,
-                                   workspace, workspace_bytes, s);
-    if (params->mode == G3D_MODE_EXACT)
-        return tdf_exact_launch(verts, vert_off, total_verts, tris, tri_off, total_tris, n_mesh, *params, *out,
-                                workspace, workspace_bytes, s);
-    set_error("tdf: unknown mode %d", params->mode);
-    return G3D_ERR_INVALID;
+    int rc = tdf_begin(total_verts, total_tris, n_mesh, *params, *out, workspace, workspace_bytes, s);
+    if (rc != G3D_OK) return rc;
+    rc = tdf_stage_tris(verts, vert_off, tris, tri_off, 0, total_tris, total_tris, n_mesh, *params, *out, workspace, s);
+    if (rc != G3D_OK) return rc;
+    return tdf_finish(vert_off, tri_off, total_tris, n_mesh, *params, *out, workspace, s);
 }
 
 int g3d_tdf_from_sdf(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog, void* cuda_stream)
@@ -192,7 +191,7 @@ int g3d_profile_enable(int32_t flags)
 {
     auto& p = g3d::g_prof;
     if ((flags & G3D_PROF_EVENTS) && !p.have_events) {
-        for (int i = 0; i <= ST_COUNT; ++i) G3D_CUDA_TRY(cudaEventCreate(&p.ev[i]));
+        for (int i = 0; i < kProfMarks; ++i) G3D_CUDA_TRY(cudaEventCreate(&p.ev[i]));
         p.have_events = true;
     }
     if ((flags & G3D_PROF_COUNT) && !p.counters) {
@@ -267,7 +266,9 @@ int g3d_context_create(int32_t device, g3d_context** ctx)
     g3d_context* c = new g3d_context();
     c->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    for (int i = 0; i < kHostChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { g3d_context_destroy(c); return cuda_fail(e, "cudaStreamCreate/cudaEventCreate"); }
     *ctx = c;
     return G3D_OK;
 }
@@ -277,6 +278,8 @@ void g3d_context_destroy(g3d_context* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
+    for (int i = 0; i < kHostChunks; ++i) if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->arena) cudaFree(c->arena);
     delete c;
 }
@@ -322,13 +325,30 @@ int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_o
     if (!base) return G3D_ERR_CUDA;
     layout(base, d, dv, dvo, dt, dto, ws);
 
+    // The meshes cross PCIe in up to 4 chunks on a copy stream; the per-triangle stage of a chunk (records,
+    // boxes, parity, band init) starts as soon as that chunk has landed, so most of the host->device time
+    // hides behind kernels. The whole-batch stage (sweeps) then runs once, on the full batch.
     cudaStream_t s = c->stream;
-    if (nv) G3D_CUDA_TRY(cudaMemcpyAsync(dv, verts, (size_t)nv * 12, cudaMemcpyHostToDevice, s));
-    if (nt) G3D_CUDA_TRY(cudaMemcpyAsync(dt, tris, (size_t)nt * 12, cudaMemcpyHostToDevice, s));
+    const int nch = n_mesh >= 64 ? kHostChunks : 1;
     G3D_CUDA_TRY(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, s));
     G3D_CUDA_TRY(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, s));
-    int rc = g3d_tdf_batch(dv, dvo, nv, dt, dto, nt, n_mesh, params, &d, ws, ws_bytes, s);
+    int rc = tdf_begin(nv, nt, n_mesh, *params, d, ws, ws_bytes, s);
     if (rc != G3D_OK) return rc;
+    for (int ch = 0; ch < nch; ++ch) {
+        const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch);
+        const int64_t v0 = vert_off[m0], v1 = vert_off[m1], t0 = tri_off[m0], t1 = tri_off[m1];
+        if (v1 > v0) G3D_CUDA_TRY(cudaMemcpyAsync(dv + 3 * v0, verts + 3 * v0, (size_t)(v1 - v0) * 12, cudaMemcpyHostToDevice, c->s_in));
+        if (t1 > t0) G3D_CUDA_TRY(cudaMemcpyAsync(dt + 3 * t0, tris + 3 * t0, (size_t)(t1 - t0) * 12, cudaMemcpyHostToDevice, c->s_in));
+        G3D_CUDA_TRY(cudaEventRecord(c->ev_in[ch], c->s_in));
+    }
+    for (int ch = 0; ch < nch; ++ch) {
+        const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch);
+        G3D_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_in[ch], 0));
+        rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], nt, n_mesh, *params, d, ws, s);
+        if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
+    }
+    rc = tdf_finish(dvo, dto, nt, n_mesh, *params, d, ws, s);
+    if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
     const size_t gb = (size_t)n_mesh * nvox * 4;
     if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf, d.sdf, gb, cudaMemcpyDeviceToHost, s));
     if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf, d.tdf, gb, cudaMemcpyDeviceToHost, s));

@@ -19,19 +19,15 @@ int  cuda_fail(cudaError_t e, const char* what);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// ---- faithful TDF (g3d_tdf.cu)
-size_t tdf_faithful_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
-int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
-                        const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
-                        int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
-                        void* ws, size_t ws_bytes, cudaStream_t stream);
-
-// ---- exact (brute-force, truncation-culled) TDF (g3d_tdf_exact.cu)
-size_t tdf_exact_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
-int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
-                     const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
-                     int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
-                     void* ws, size_t ws_bytes, cudaStream_t stream);
+// ---- TDF, both modes (g3d_tdf.cu), in three phases (see the definitions)
+size_t tdf_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
+int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
+              const g3d_tdf_outputs& out, void* ws, size_t ws_bytes, cudaStream_t stream);
+int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* tris, const int64_t* tri_off,
+                   int64_t t0, int64_t t1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
+                   const g3d_tdf_outputs& out, void* ws, cudaStream_t stream);
+int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tris, int32_t n_mesh,
+               const g3d_tdf_params& p, const g3d_tdf_outputs& out, void* ws, cudaStream_t stream);
 
 int tdf_from_sdf_launch(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog,
                         cudaStream_t stream);
@@ -46,6 +42,7 @@ int sm_count();
 
 // ---- profiling hooks (g3d_capi.cu); no-ops unless g3d_profile_enable was called on this thread
 enum { ST_FILL = 0, ST_PREP, ST_INIT, ST_ORDER, ST_SWEEP, ST_FINAL, ST_EXACT, ST_RAYCAST, ST_COUNT };
+constexpr int kProfMarks = 40;                      // events per call (chunked calls mark a stage several times)
 void prof_begin(cudaStream_t s);                    // start of an API call: resets marks + counters
 void prof_mark(int stage, cudaStream_t s);          // call right AFTER launching the kernel(s) of `stage`
 unsigned long long* prof_counters();                // device u64[4] or nullptr

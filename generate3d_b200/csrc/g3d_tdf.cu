@@ -152,11 +152,11 @@ __device__ __forceinline__ int mesh_of(const int64_t* off, int n_mesh, int64_t t
 __global__ void __launch_bounds__(256)
 tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ vert_off,
                 const uint32_t* __restrict__ tris, const int64_t* __restrict__ tri_off,
-                int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
+                int64_t t_first, int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
                 int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status,
                 float4* __restrict__ aabb_out, float4* __restrict__ fast_out)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t t = t_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_tris) return;
     int m = mesh_of(tri_off, n_mesh, t);
     int64_t v0 = vert_off[m], nv = vert_off[m + 1] - v0;
@@ -288,7 +288,7 @@ __device__ __forceinline__ void init_eval_item(uint32_t t, uint32_t pos, const f
 
 __global__ void __launch_bounds__(256)
 tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
-                const int64_t* __restrict__ tri_off, int64_t total_tris, g3d_tdf_params P,
+                const int64_t* __restrict__ tri_off, int64_t t_first, int64_t total_tris, g3d_tdf_params P,
                 u64* __restrict__ key, float far, u64* counter)
 {
     __shared__ uint32_t s_qt[8][64], s_qp[8][64];
@@ -300,7 +300,7 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t nvox = nvox_of(P);
-    for (int64_t t = warp; t < total_tris; t += nwarp) {
+    for (int64_t t = t_first + warp; t < total_tris; t += nwarp) {
         int4 b = __ldg(box + t);
         int i0 = b.x & 0xffff, i1 = b.x >> 16, j0 = b.y & 0xffff, j1 = b.y >> 16, k0 = b.z & 0xffff, k1 = b.z >> 16;
         int bi = i1 - i0 + 1, bj = j1 - j0 + 1, bk = k1 - k0 + 1;
@@ -734,11 +734,6 @@ int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, c
 }
 }  // namespace
 
-size_t tdf_faithful_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
-{
-    return carve(nullptr, n_mesh, total_tris, p).bytes;
-}
-
 int tdf_validate(int32_t n_mesh, int64_t total_verts, int64_t total_tris, const g3d_tdf_params& p)
 {
     if (n_mesh < 0 || total_verts < 0 || total_tris < 0) { set_error("negative size"); return G3D_ERR_INVALID; }
@@ -752,17 +747,22 @@ int tdf_validate(int32_t n_mesh, int64_t total_verts, int64_t total_tris, const 
     return G3D_OK;
 }
 
-int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
-                        const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
-                        int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
-                        void* ws, size_t ws_bytes, cudaStream_t stream)
+// The work of one batch call in three phases, so that the host-buffer front end can start on the first
+// triangles while the rest of the batch is still crossing PCIe:
+//   tdf_begin        validate, carve the workspace, initialise keys / parity / change bytes
+//   tdf_stage_tris   per-triangle work for triangles [t0, t1): records, boxes, parity (+ band init, faithful mode)
+//   tdf_finish       the whole-batch part: sweeps or the exact kernel, then the fused epilogue
+int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
+              const g3d_tdf_outputs& out, void* ws, size_t ws_bytes, cudaStream_t stream)
 {
     int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
     if (rc != G3D_OK) return rc;
+    if (p.mode != G3D_MODE_FAITHFUL && p.mode != G3D_MODE_EXACT) { set_error("tdf: unknown mode %d", p.mode); return G3D_ERR_INVALID; }
     if (n_mesh == 0) return G3D_OK;
-    TdfWs w = carve(ws, n_mesh, total_tris, p);
-    if (w.bytes > ws_bytes || (!ws && w.bytes)) {
-        set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+    const size_t need = p.mode == G3D_MODE_EXACT ? exact::carve(nullptr, n_mesh, total_tris, p).bytes
+                                                 : carve(nullptr, n_mesh, total_tris, p).bytes;
+    if (need > ws_bytes || (!ws && need)) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return G3D_ERR_WORKSPACE;
     }
     const int sms = sm_count();
@@ -770,107 +770,113 @@ int tdf_faithful_launch(const float* verts, const int64_t* vert_off, int64_t tot
     const float far = (float)(p.ni + p.nj + p.nk) * p.dx;                  // cpp:123
     union { float f; uint32_t u; } fb; fb.f = far;
     const u64 init = ((u64)fb.u << 32) | 0xffffffffull;                      // closest_tri = -1
-
     prof_begin(stream);
-    u64* cnt = prof_counters();
-    G3D_CUDA_TRY(cudaMemsetAsync(w.chg, 0, (size_t)n_mesh * nvox, stream));
+    u64* key; uint32_t* parity;
+    if (p.mode == G3D_MODE_EXACT) {
+        exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
+        key = w.key; parity = w.parity;
+    } else {
+        TdfWs w = carve(ws, n_mesh, total_tris, p);
+        key = w.key; parity = w.parity;
+        G3D_CUDA_TRY(cudaMemsetAsync(w.chg, 0, (size_t)n_mesh * nvox, stream));
+    }
     tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
-        w.key, n_mesh * nvox, init, w.parity, n_mesh * pw, out.status, n_mesh,
+        key, n_mesh * nvox, init, parity, n_mesh * pw, out.status, n_mesh,
         (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
     prof_mark(ST_FILL, stream);
-    if (total_tris > 0) {
-        tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* tris, const int64_t* tri_off,
+                   int64_t t0, int64_t t1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
+                   const g3d_tdf_outputs& out, void* ws, cudaStream_t stream)
+{
+    if (n_mesh == 0 || t1 <= t0) return G3D_OK;
+    const int sms = sm_count();
+    const float far = (float)(p.ni + p.nj + p.nk) * p.dx;
+    if (p.mode == G3D_MODE_EXACT) {
+        exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
+        tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
+            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb, w.fast);
         prof_mark(ST_PREP, stream);
-        tdf_init_kernel<<<grid_for(total_tris * 32, 256, sms * 32), 256, 0, stream>>>(
-            w.tri, w.box, tri_off, total_tris, p, w.key, far, cnt);
+    } else {
+        TdfWs w = carve(ws, n_mesh, total_tris, p);
+        tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
+            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr);
+        prof_mark(ST_PREP, stream);
+        tdf_init_kernel<<<grid_for((t1 - t0) * 32, 256, sms * 32), 256, 0, stream>>>(
+            w.tri, w.box, tri_off, t0, t1, p, w.key, far, prof_counters());
         prof_mark(ST_INIT, stream);
+    }
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tris, int32_t n_mesh,
+               const g3d_tdf_params& p, const g3d_tdf_outputs& out, void* ws, cudaStream_t stream)
+{
+    if (n_mesh == 0) return G3D_OK;
+    u64* cnt = prof_counters();
+    const u64* key; const uint32_t* parity;
+    if (p.mode == G3D_MODE_EXACT) {
+        exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
+        key = w.key; parity = w.parity;
+        if (total_tris > 0) {
+            constexpr int WX = exact::kWX, WY = exact::kWY, WZ = exact::kWZ, NT = WX * WY * WZ * 32, TILE = exact::kTile;
+            const int nbx = (p.ni + WX * 4 - 1) / (WX * 4), nby = (p.nj + WY * 4 - 1) / (WY * 4), nbz = (p.nk + WZ * 2 - 1) / (WZ * 2);
+            const int64_t nblocks = (int64_t)n_mesh * nbx * nby * nbz;
+            if (nblocks >= (int64_t)INT_MAX) { set_error("exact: too many blocks in one call (%lld)", (long long)nblocks); return G3D_ERR_INVALID; }
+            const float far = (float)(p.ni + p.nj + p.nk) * p.dx;
+            // distances up to R matter: trunc is in output units (phi * out_scale)
+            float R = __builtin_inff();
+            if (p.trunc < 3.0e38f && p.out_scale > 0.f) R = p.trunc / p.out_scale * 1.0001f;
+            static int strict = -1;                 // G3D_EXACT_STRICT=1: single-stage kernel (every pair evaluated faithfully)
+            if (strict < 0) { const char* e = getenv("G3D_EXACT_STRICT"); strict = (e && atoi(e)) ? 1 : 0; }
+            if (strict) {
+                const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
+                G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                exact::tdf_exact_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+                    w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
+            } else {
+                // filter margins of the two-stage kernel, scaled by the extent of the coordinates involved
+                float S = 0.f;
+                const int dims[3] = { p.ni, p.nj, p.nk };
+                for (int a = 0; a < 3; ++a) {
+                    S = fmaxf(S, fabsf(p.origin[a]));
+                    S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
+                }
+                const float eta = 2e-4f * S, kappa = 1e-6f * S * S;
+                const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4 + (size_t)(NT / 32) * 64 * 4;
+                G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                exact::tdf_exact2_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
+                    w.tri, w.fast, w.aabb, tri_off, w.parity, w.key, p, R, far, eta, kappa, nbx, nby, nbz, cnt);
+            }
+            prof_mark(ST_EXACT, stream);
+        }
+    } else {
+        TdfWs w = carve(ws, n_mesh, total_tris, p);
+        key = w.key; parity = w.parity;
         const int nlev = nlev_of(p);
-        if (nlev > 0) {
+        if (total_tris > 0 && nlev > 0) {
             size_t smem = (size_t)(nlev + 1) * 4;
             tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start);
             prof_mark(ST_ORDER, stream);
-            rc = launch_sweep(n_mesh, nlev, w, tri_off, p, cnt, stream);
+            int rc = launch_sweep(n_mesh, nlev, w, tri_off, p, cnt, stream);
             if (rc != G3D_OK) return rc;
             prof_mark(ST_SWEEP, stream);
         }
     }
     tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
-        w.key, w.parity, vert_off, tri_off, n_mesh, p, out, 1);
+        key, parity, vert_off, tri_off, n_mesh, p, out, 1);
     prof_mark(ST_FINAL, stream);
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
 }
 
-size_t tdf_exact_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
+size_t tdf_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
 {
-    return exact::carve(nullptr, n_mesh, total_tris, p).bytes;
-}
-
-int tdf_exact_launch(const float* verts, const int64_t* vert_off, int64_t total_verts,
-                     const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
-                     int32_t n_mesh, const g3d_tdf_params& p, const g3d_tdf_outputs& out,
-                     void* ws, size_t ws_bytes, cudaStream_t stream)
-{
-    int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
-    if (rc != G3D_OK) return rc;
-    if (n_mesh == 0) return G3D_OK;
-    exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
-    if (w.bytes > ws_bytes || (!ws && w.bytes)) {
-        set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
-        return G3D_ERR_WORKSPACE;
-    }
-    constexpr int WX = exact::kWX, WY = exact::kWY, WZ = exact::kWZ, NT = WX * WY * WZ * 32, TILE = exact::kTile;
-    const int nbx = (p.ni + WX * 4 - 1) / (WX * 4), nby = (p.nj + WY * 4 - 1) / (WY * 4), nbz = (p.nk + WZ * 2 - 1) / (WZ * 2);
-    const int64_t nblocks = (int64_t)n_mesh * nbx * nby * nbz;
-    if (nblocks >= (int64_t)INT_MAX) { set_error("exact: too many blocks in one call (%lld)", (long long)nblocks); return G3D_ERR_INVALID; }
-    const int sms = sm_count();
-    const int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32;
-    const float far = (float)(p.ni + p.nj + p.nk) * p.dx;
-    union { float f; uint32_t u; } fb; fb.f = far;
-    const u64 init = ((u64)fb.u << 32) | 0xffffffffull;
-    // distances up to R matter: trunc is in output units (phi * out_scale)
-    float R = __builtin_inff();
-    if (p.trunc < 3.0e38f && p.out_scale > 0.f) R = p.trunc / p.out_scale * 1.0001f;
-
-    prof_begin(stream);
-    u64* cnt = prof_counters();
-    tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
-        w.key, n_mesh * nvox, init, w.parity, n_mesh * pw, out.status, n_mesh,
-        (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
-    prof_mark(ST_FILL, stream);
-    if (total_tris > 0) {
-        tdf_prep_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, total_tris, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb, w.fast);
-        prof_mark(ST_PREP, stream);
-        static int strict = -1;                     // G3D_EXACT_STRICT=1: single-stage kernel (every pair evaluated faithfully)
-        if (strict < 0) { const char* e = getenv("G3D_EXACT_STRICT"); strict = (e && atoi(e)) ? 1 : 0; }
-        if (strict) {
-            const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
-            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            exact::tdf_exact_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
-                w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
-        } else {
-            // filter margins of the two-stage kernel, scaled by the extent of the coordinates involved
-            float S = 0.f;
-            const int dims[3] = { p.ni, p.nj, p.nk };
-            for (int a = 0; a < 3; ++a) {
-                S = fmaxf(S, fabsf(p.origin[a]));
-                S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
-            }
-            const float eta = 2e-4f * S, kappa = 1e-6f * S * S;
-            const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4 + (size_t)(NT / 32) * 64 * 4;
-            G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            exact::tdf_exact2_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
-                w.tri, w.fast, w.aabb, tri_off, w.parity, w.key, p, R, far, eta, kappa, nbx, nby, nbz, cnt);
-        }
-        prof_mark(ST_EXACT, stream);
-    }
-    tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
-        w.key, w.parity, vert_off, tri_off, n_mesh, p, out, 1);
-    prof_mark(ST_FINAL, stream);
-    G3D_CUDA_TRY(cudaGetLastError());
-    return G3D_OK;
+    return p.mode == G3D_MODE_EXACT ? exact::carve(nullptr, n_mesh, total_tris, p).bytes : carve(nullptr, n_mesh, total_tris, p).bytes;
 }
 
 int tdf_from_sdf_launch(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog, cudaStream_t stream)
