@@ -414,7 +414,7 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 //      per lane), and the owners then replay the results in neighbour order.
 constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+using exact::prefetch_l1;
 
 __device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
 {
@@ -847,7 +847,7 @@ int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tr
                     S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
                 }
                 const float eta = 2e-4f * S, kappa = 1e-6f * S * S;
-                const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4 + (size_t)(NT / 32) * 64 * 4;
+                const size_t smem = (size_t)3 * TILE * 32 + (size_t)2 * TILE * 4 + 3 * 8 + 4 * 4 + (size_t)(NT / 32) * 4 + (size_t)(NT / 32) * 64 * 4;
                 G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 exact::tdf_exact2_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
                     w.tri, w.fast, w.aabb, tri_off, w.parity, w.key, p, R, far, eta, kappa, nbx, nby, nbz, cnt);

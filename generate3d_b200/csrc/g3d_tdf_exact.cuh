@@ -26,11 +26,15 @@
 
 namespace exact {
 
-// block shape in warps (each warp = a 4x4x2 brick) and triangle-box tile size. Small blocks win: the two block
-// barriers per tile cost the slowest brick's time, and a brick next to the surface does thousands of evaluations
-// while a far one does none (measured on B200, 1,024 meshes: 2x2x4 warps 105 ms, barrier stall 8.1 per issue).
+// block shape in warps (each warp = a 4x4x2 brick) and triangle-box tile size. Small blocks and small tiles win:
+// a block barrier costs the slowest brick's time (a brick next to the surface rates thousands of pairs, a far one
+// none), and occupancy is bounded by the tile stages in shared memory. Measured on B200, 1,024 meshes, two-stage
+// kernel: 2x2x4 warps / 1024 boxes 105 ms; 2x1x2 / 512 (two barriers per tile) 67.7; one barrier per tile with
+// three stages: 2x1x2 / 512 90.4, / 256 56.4, / 128 67.1; 2x2x2 / 256 58.9; prefetching the next survivor's
+// record costs more than it hides (60.2 vs 56.4).
 constexpr int kWX = 2, kWY = 1, kWZ = 2;
-constexpr int kTile = 512;
+constexpr int kTile = 256;
+constexpr bool kPrefetchNext = false;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,6 +63,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "WAIT_DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // squared distance between two axis-aligned boxes (0 when they overlap); FMA is fine here, the
 // result only feeds a conservative comparison
@@ -288,14 +294,15 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                   const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
                   g3d_tdf_params P, float R, float far, float eta, float kappa, int nbx, int nby, int nbz, u64* counter)
 {
-    constexpr int NT = WX * WY * WZ * 32;
+    constexpr int NT = WX * WY * WZ * 32, NW = NT / 32;
     constexpr int BX = WX * 4, BY = WY * 4, BZ = WZ * 2;                      // nodes per block and axis
     extern __shared__ __align__(128) unsigned char s_raw[];
-    float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [2][TILE * 2]
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 2 * TILE * 32);    // [TILE]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_list + TILE);             // [2]
-    int* s_count = reinterpret_cast<int*>(s_bar + 2);                         // [2]
-    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_count + 2);             // [NT/32][64]  t << 5 | owner lane
+    float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [3][TILE * 2]  TMA stages
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 3 * TILE * 32);    // [2][TILE]      block-level survivors
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_list + 2 * TILE);         // [3]
+    int* s_count = reinterpret_cast<int*>(s_bar + 3);                         // [3] (+1 pad)
+    float* s_wb = reinterpret_cast<float*>(s_count + 4);                      // [NW] running bound^2 of each brick
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_wb + NW);               // [NW][64]  t << 5 | owner lane
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t* q = s_queue + warp * 64;
@@ -335,8 +342,13 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
     const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
     const V3 blk_lo = node_pos(cbx * BX, cby * BY, cbz * BZ, P);
     const V3 blk_hi = node_pos(min(cbx * BX + BX - 1, ni - 1), min(cby * BY + BY - 1, nj - 1), min(cbz * BZ + BZ - 1, nk - 1), P);
-    const int any_inside = __syncthreads_or(inside ? 1 : 0);
-    const float blk_bound2 = any_inside ? INF : fmaf(R + eta, R + eta, kappa) * 1.001f;
+
+    auto warp_bound2 = [&]() {                      // largest distance^2 that still matters to any voxel of the brick
+        float v = lim2;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+        return v * 1.001f;
+    };
 
     const int64_t t0 = tri_off[mesh];
     const int T = (int)(tri_off[mesh + 1] - t0);
@@ -368,32 +380,39 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
         }
         __syncwarp();
     };
+    auto issue_tile = [&](int tile) {               // thread 0: TMA bulk copy of one tile of boxes into stage tile % 3
+        const int sg = tile % 3;
+        const uint32_t bytes = (uint32_t)min(TILE, T - tile * TILE) * 32u;
+        mbar_expect_tx(&s_bar[sg], bytes);
+        bulk_g2s(s_box + sg * TILE * 2, Bm + 2 * (int64_t)tile * TILE, bytes, &s_bar[sg]);
+    };
 
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
         mbar_fence_init();
-        s_count[0] = s_count[1] = 0;
+        s_count[0] = s_count[1] = s_count[2] = 0;
     }
+    { const float wb = warp_bound2(); if (lane == 0) s_wb[warp] = wb; }
     __syncthreads();
-    if (tid == 0 && ntile > 0) {
-        uint32_t bytes = (uint32_t)min(TILE, T) * 32u;
-        mbar_expect_tx(&s_bar[0], bytes);
-        bulk_g2s(s_box, Bm, bytes, &s_bar[0]);
+    if (tid == 0) {
+        if (ntile > 0) issue_tile(0);
+        if (ntile > 1) issue_tile(1);
     }
+    // One block barrier per tile: [phase A of tile it] barrier [phase B of tile it], with three box stages, two
+    // survivor lists and three counters so that a fast warp may already run phase A of the next tile.
     for (int it = 0; it < ntile; ++it) {
-        const int st = it & 1;
-        const int tile_base = it * TILE;
-        const int tn = min(TILE, T - tile_base);
-        if (tid == 0 && it + 1 < ntile) {
-            uint32_t bytes = (uint32_t)min(TILE, T - (tile_base + TILE)) * 32u;
-            mbar_expect_tx(&s_bar[st ^ 1], bytes);
-            bulk_g2s(s_box + (st ^ 1) * TILE * 2, Bm + 2 * (int64_t)(tile_base + TILE), bytes, &s_bar[st ^ 1]);
-        }
-        mbar_wait(&s_bar[st], (it >> 1) & 1);
-        const float4* box = s_box + st * TILE * 2;
+        const int sg = it % 3, lb = it & 1;
+        const int tn = min(TILE, T - it * TILE);
+        mbar_wait(&s_bar[sg], (it / 3) & 1);
+        const float4* box = s_box + sg * TILE * 2;
+        uint32_t* list = s_list + lb * TILE;
 
-        // ---- phase A: block-level cull
+        // ---- phase A: block-level cull against the largest running bound of the block's bricks
+        float blk_bound2 = s_wb[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) blk_bound2 = fmaxf(blk_bound2, s_wb[w]);
         for (int q0 = warp * 32; q0 < tn; q0 += NT) {
             int qq = q0 + lane;
             bool pass = false;
@@ -404,25 +423,23 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
             uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (m) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&s_count[st], __popc(m));
+                if (lane == 0) base = atomicAdd(&s_count[sg], __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)qq;
+                if (pass) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)qq;
             }
         }
+        if (tid == 0) s_count[(it + 1) % 3] = 0;    // last read in phase B of tile it-2, next written after the barrier
         __syncthreads();
-        const int nlist = s_count[st];
-        if (tid == 0) s_count[st ^ 1] = 0;
+        if (tid == 0 && it + 2 < ntile) issue_tile(it + 2);   // its stage was last read in tile it-1
+        const int nlist = s_count[sg];
 
         // ---- phase B: brick-level cull with the running bound, stage 1 on the survivors
         for (int l0 = 0; l0 < nlist; l0 += 32) {
-            float bound2 = lim2;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) bound2 = fmaxf(bound2, __shfl_xor_sync(0xffffffffu, bound2, d));
-            bound2 *= 1.001f;
+            const float bound2 = warp_bound2();
             uint32_t tq = 0;                         // the triangle's own index rides in lo.w of its box
             bool pass = false;
             if (l0 + lane < nlist) {
-                const int qq = (int)s_list[l0 + lane];
+                const int qq = (int)list[l0 + lane];
                 const float4 lo = box[2 * qq];
                 tq = __float_as_uint(lo.w);
                 pass = box_gap2(lo, box[2 * qq + 1], brick_lo, brick_hi) <= bound2;
@@ -433,6 +450,10 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const uint32_t t = __shfl_sync(0xffffffffu, tq, src);
+                if (kPrefetchNext && m) {           // pull the next survivor's record while this one is rated
+                    const uint32_t tn2 = __shfl_sync(0xffffffffu, tq, __ffs(m) - 1);
+                    if (lane < 2) prefetch_l1(reinterpret_cast<const char*>(Fm + 5 * (int64_t)tn2) + lane * 64);
+                }
                 bool flagged;
                 const float a2 = fast_dist2(gx, Fm + 5 * (int64_t)t, flagged);
                 n_pairs += valid ? 1 : 0;
@@ -450,7 +471,7 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                 }
             }
         }
-        __syncthreads();
+        { const float wb = warp_bound2(); if (lane == 0) s_wb[warp] = wb; }
     }
     if (qn > 0) flush(0, qn);
     if (valid) {
