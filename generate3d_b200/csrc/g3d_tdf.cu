@@ -758,6 +758,10 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
     if (rc != G3D_OK) return rc;
     if (p.mode != G3D_MODE_FAITHFUL && p.mode != G3D_MODE_EXACT) { set_error("tdf: unknown mode %d", p.mode); return G3D_ERR_INVALID; }
+    if (p.mode == G3D_MODE_EXACT && total_tris >= ((int64_t)1 << 27)) {   // stage-2 queue entries are t << 5 | lane
+        set_error("exact mode: at most 2^27 - 1 triangles per call, got %lld", (long long)total_tris);
+        return G3D_ERR_INVALID;
+    }
     if (n_mesh == 0) return G3D_OK;
     const size_t need = p.mode == G3D_MODE_EXACT ? exact::carve(nullptr, n_mesh, total_tris, p).bytes
                                                  : carve(nullptr, n_mesh, total_tris, p).bytes;

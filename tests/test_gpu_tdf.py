@@ -287,3 +287,52 @@ def test_cadvoxelization_dropin_writes_reference_files(g3d, oracle, tmp_path):
         assert keep[mid]["tdf"].is_cuda
     done2, _ = CV.voxelize_models(models, params["shapenet_voxelized"], chunk=4)      # resume: nothing left but the broken one
     assert done2 == 0
+
+
+def test_cabi_error_paths(g3d):
+    """Bad arguments come back as error codes with a message, never as a crash or a silent fallback."""
+    L = g3d.lib()
+    p = g3d.TdfParams()
+    g2w = np.zeros(16, np.float32)
+    g3d.check(L.g3d_dfgen_geometry(32, 0, 1, None, None, C.byref(p), g2w.ctypes.data))
+    p.trunc, p.occ_thresh, p.mode = 3.0, 1.0, 0
+    v = torch.zeros((3, 3), device="cuda")
+    t = torch.zeros((1, 3), dtype=torch.int32, device="cuda")
+    off = torch.tensor([0, 3], device="cuda"); toff = torch.tensor([0, 1], device="cuda")
+    sdf = torch.empty((1, 32, 32, 32), device="cuda")
+    o = g3d.TdfOutputs(); o.sdf = sdf.data_ptr()
+    need = L.g3d_tdf_workspace_bytes(1, 3, 1, C.byref(p))
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    args = lambda wsb, mode=0: (v.data_ptr(), off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), 1, 1, C.byref(p), C.byref(o), ws.data_ptr(), wsb, None)
+    assert L.g3d_tdf_batch(*args(need)) == 0
+    assert L.g3d_tdf_batch(*args(need // 2)) == -3 and b"workspace" in L.g3d_last_error()      # G3D_ERR_WORKSPACE
+    p.mode = 7
+    assert L.g3d_tdf_batch(*args(need)) == -1 and b"mode" in L.g3d_last_error()
+    p.mode, p.ni = 0, 0
+    assert L.g3d_tdf_batch(*args(need)) == -1
+    p.ni = 32
+    assert L.g3d_tdf_batch(None, off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), 1, 1, C.byref(p), C.byref(o), ws.data_ptr(), need, None) == -1
+    assert L.g3d_raycast_batch(None, None, 1, 64, 64, 525.0, 32.0, 32.0, 511, 32, None, None, None, None) == -1
+    assert L.g3d_raycast_batch(v.data_ptr(), v.data_ptr(), 1, 4096, 4096, 525.0, 32.0, 32.0, 511, 32, sdf.data_ptr(), None, None, None) == -1
+    assert b"shared memory" in L.g3d_last_error()
+    assert L.g3d_occ_to_df_batch(sdf.data_ptr(), 1, 100, 0, 3.0, 3.0, sdf.data_ptr(), None) == -1
+    torch.cuda.synchronize()                                     # nothing above poisoned the context
+    assert L.g3d_tdf_batch(*args(need)) == 0
+    torch.cuda.synchronize()
+
+
+def test_faithful_single_huge_triangle_and_outside_mesh(g3d, oracle):
+    """One triangle spanning the whole grid (band box = every node, the integer-division path of the init) and a
+    mesh lying completely outside the unit cube (boxes clamp to the boundary layer)."""
+    from generate3d_b200 import dfgen
+    g = oracle.dfgen_geometry(32)
+    big_v = np.float32([[-2, -2, 0.01], [2, -2, 0.02], [0, 3, -0.03], [0.1, 0.1, 0.4], [0.2, 0.1, 0.4], [0.1, 0.3, 0.45]])
+    big_t = np.uint32([[0, 1, 2], [3, 4, 5]])
+    out_v, out_t = S.table_mesh(2, 70)
+    out_v = out_v + np.float32([1.7, 0, 0])
+    for v, t in ((big_v, big_t), (out_v, out_t)):
+        want = oracle.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32)
+        phi, ct = dfgen.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32, return_closest_tri=True)
+        assert np.array_equal(_bits(phi.cpu().numpy()), _bits(want["phi"]))
+        assert np.array_equal(ct.cpu().numpy(), want["closest_tri"])
