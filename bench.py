@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true")
     return ap.parse_args()
 
 
@@ -346,6 +347,37 @@ def run_b200(args, rank, world, local):
     }
     ray_launches = max(args.steps, 20) + args.steps
 
+    # ---- "next" rows: occupancy -> chamfer DF over the batch's GT occupancy, colour raycast of 20 views
+    next_rows = None
+    if not args.no_next_rows:
+        from generate3d_b200 import data_utils
+        occ_in = dfgen.tdf_batch(dV, dvoff, dT, dtoff, dim=DIM, outputs=("occ_f32",))["occ_f32"].unsqueeze(1)   # [M,1,32,32,32]
+
+        def timed(fn, steps):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            barrier()
+            return shard.all_reduce_max(a.elapsed_time(b) / steps, dev)
+        ms_df = timed(lambda: data_utils.occs_to_dfs(occ_in, TRUNC, pred=False), max(args.steps, 10))
+        d512, p512 = S.depth_views(20, 512, 512)
+        col = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (20, 512, 512, 3), dtype=np.uint8)).to(dev)
+        dd512, dp512 = torch.from_numpy(d512).to(dev), torch.from_numpy(p512).to(dev)
+        ms_col = timed(lambda: raytracing.raycast_color_batch(dd512, col, dp512), max(args.steps, 10))
+        next_rows = {
+            "occ_to_df": {"value": world * M / (ms_df * 1e-3), "unit": "grids/s", "ms_per_step": ms_df,
+                          "workload": "%d GT occupancy grids 32^3 per GPU -> chamfer DF (data_utils.occs_to_dfs)" % M,
+                          "bytes_per_grid": 2 * DIM ** 3 * 4, "achieved_gbs": M * 2 * DIM ** 3 * 4 / (ms_df * 1e-3) / 1e9},
+            "raycast_color": {"value": world * 20 * 512 * 512 / (ms_col * 1e-3), "unit": "rays/s", "ms_per_step": ms_col,
+                              "workload": "20 views 512x512 colour + depth -> 32^3 mean-colour grids (raytracing.raycast)"},
+        }
+        ray_launches += 2 * (max(args.steps, 10) + 3)
+
     # ---- e2e through the host-buffer C ABI: pinned host arrays in, sdf + occupancy bits + status out
     e2e = None
     if not args.no_e2e:
@@ -404,7 +436,7 @@ def run_b200(args, rank, world, local):
                        "trunc": TRUNC, "mode": args.mode, "outputs": list(outputs),
                        "l2": "inputs %.0f MB + outputs %.0f MB per step, larger than the 126 MB L2 (no explicit flush)" % (input_mb, M * DIM ** 3 * 12.125 / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": tdf_launches + ray_launches, "roofline": roofline,
-            "cpu_baseline": cpu, "stages_ms": stages_ms, "evals_per_step": evals, "other_mode": other_mode, "raycast": raycast,
+            "cpu_baseline": cpu, "stages_ms": stages_ms, "evals_per_step": evals, "other_mode": other_mode, "raycast": raycast, "next_rows": next_rows,
             "pair_rate_nominal_per_s": world * M * DIM ** 3 * 60 * args.n ** 2 / (ms_step * 1e-3),
         }
         print(json.dumps(line), flush=True)

@@ -54,6 +54,8 @@ SYMBOLS = {
     "g3d_read_df": (C.c_int, [C.c_char_p, _vp, _vp, _vp, _vp, _i64]),
     "g3d_occ_to_df_batch": (C.c_int, [_vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
     "g3d_raycast_color_batch": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _i32, _vp, _vp]),
+    "g3d_raymarch": (C.c_int, [_vp, _vp, _i32, _i32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i32,
+                               _vp, _vp, _vp, _vp]),
     "g3d_profile_enable": (C.c_int, [_i32]),
     "g3d_profile_read": (C.c_int, [_vp, _vp]),
     "g3d_probe_fp32_tflops": (C.c_int, [_vp, _vp]),

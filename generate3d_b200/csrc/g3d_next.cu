@@ -174,3 +174,77 @@ extern "C" int g3d_raycast_color_batch(const uint8_t* depth, const uint8_t* colo
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
 }
+
+// ------------------------------------------------------------------------ per-pixel ray march ----
+// the older raytracing_approach1.py:13-51. Every pixel shoots a ray from the
+// z_near plane through a camera-aligned voxel box and marks the voxels it crosses in half-voxel steps; a voxel
+// keeps the colour of the LAST pixel (u outer, v inner loop) that touched it. The reference does this in float64
+// numpy scalars, so the march is replayed in double precision with explicitly rounded operations; "last writer"
+// becomes an atomicMax over u*H+v per voxel.
+namespace g3d {
+namespace {
+
+__global__ void __launch_bounds__(256)
+raymarch_kernel(const uint8_t* __restrict__ depth, int H, int W, double cx, double cy, double focal, double z_near,
+                double grid_size, int dim, uint32_t* __restrict__ last_px)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const int u = p / H, v = p - u * H;              // u outer, v inner (raytracing_approach1.py:29-30)
+    if (depth[(size_t)v * W + u] == 0) return;       // :45 -- such a pixel never writes
+    const double vs = grid_size / (double)dim;       // voxel_grid.py:14
+    const double minx = -grid_size / 2, miny = -grid_size / 2, minz = -z_near;           // voxel_grid.py:167-168
+    const double maxx = __dadd_rn(minx, grid_size), maxy = __dadd_rn(miny, grid_size);
+    const double maxz = __dsub_rn(__dadd_rn(minz, grid_size), __dmul_rn(2.0, grid_size)); // voxel_grid.py:16-19
+    const double x = __ddiv_rn(__dmul_rn((double)u - cx, z_near), focal);                // :31-32
+    const double y = __ddiv_rn(__dmul_rn((double)v - cy, z_near), focal);
+    double rx = x, ry = -y, rz = -z_near;
+    double len = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)));   // :34
+    const double ux = __ddiv_rn(rx, len), uy = __ddiv_rn(ry, len), uz = __ddiv_rn(rz, len);
+    const double half = vs / 2;
+    for (int guard = 0; guard < (1 << 20); ++guard) {
+        if (!(minx <= rx && rx <= maxx && miny <= ry && ry <= maxy && maxz <= rz && rz <= minz)) break;   // voxel_grid.py:55-63
+        const int gi = (int)__ddiv_rn(__dsub_rn(rx, minx), vs);                          // voxel_grid.py:42-47
+        const int gj = (int)__ddiv_rn(__dsub_rn(ry, miny), vs);
+        const int gk = (int)__ddiv_rn(-__dsub_rn(rz, minz), vs);
+        if (gi <= dim - 1 && gj <= dim - 1 && gk <= dim - 1)                             // voxel_grid.py:49-50
+            atomicMax(last_px + ((size_t)gi * dim + gj) * dim + gk, (uint32_t)p + 1u);
+        len = __dadd_rn(len, half);                                                      // :50-51
+        rx = __dmul_rn(ux, len); ry = __dmul_rn(uy, len); rz = __dmul_rn(uz, len);
+    }
+}
+
+__global__ void raymarch_resolve_kernel(const uint32_t* __restrict__ last_px, const uint8_t* __restrict__ color, int H, int W,
+                                        int n, uint8_t* __restrict__ occ, uint8_t* __restrict__ rgb)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t k = last_px[q];
+    occ[q] = k ? 1 : 0;
+    uint8_t r = 0, g = 0, b = 0;
+    if (k) {
+        const int p = (int)(k - 1), u = p / H, v = p - u * H;
+        const uint8_t* c = color + ((size_t)v * W + u) * 3;
+        r = c[0]; g = c[1]; b = c[2];
+    }
+    rgb[3 * q] = r; rgb[3 * q + 1] = g; rgb[3 * q + 2] = b;
+}
+
+}  // namespace
+}  // namespace g3d
+
+extern "C" int g3d_raymarch(const uint8_t* depth, const uint8_t* color, int32_t H, int32_t W, double cx, double cy,
+                            double focal, double z_near, double z_far, int32_t dim, uint8_t* occ, uint8_t* rgb,
+                            uint32_t* scratch, void* cuda_stream)
+{
+    if (H < 1 || W < 1 || dim < 1 || dim > 1024 || !(focal > 0) || !(z_near > 0)) { set_error("raymarch: bad arguments"); return G3D_ERR_INVALID; }
+    if (!depth || !color || !occ || !rgb || !scratch) { set_error("raymarch: NULL pointer"); return G3D_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int n = dim * dim * dim;
+    const double grid_size = fabs(z_far - z_near);                                       // voxel_grid.py:166
+    G3D_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t)n * 4, s));
+    raymarch_kernel<<<(H * W + 255) / 256, 256, 0, s>>>(depth, H, W, cx, cy, focal, z_near, grid_size, dim, scratch);
+    raymarch_resolve_kernel<<<(n + 255) / 256, 256, 0, s>>>(scratch, color, H, W, n, occ, rgb);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}

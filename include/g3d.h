@@ -188,6 +188,15 @@ int g3d_raycast_color_batch(const uint8_t* depth, const uint8_t* color, const fl
                             int32_t H, int32_t W, float focal, float cx, float cy, int32_t clamp_max,
                             int32_t dim, uint16_t* out, void* cuda_stream);
 
+/* Per-pixel ray march (raytracing_approach1.py:13-51, the approach raytracing.py superseded): rays start on
+ * the z_near plane and cross a camera-aligned box of side |z_far - z_near| in half-voxel steps, in float64
+ * like the reference; a voxel keeps the colour of the last pixel (u outer, v inner) that touched it.
+ * depth u8 [H,W], color u8 [H,W,3]; occ u8 [dim^3] and rgb u8 [dim^3,3] in [x][y][z] order (VoxelGrid's
+ * own indexing); scratch u32 [dim^3]. Device pointers. */
+int g3d_raymarch(const uint8_t* depth, const uint8_t* color, int32_t H, int32_t W, double cx, double cy,
+                 double focal, double z_near, double z_far, int32_t dim, uint8_t* occ, uint8_t* rgb,
+                 uint32_t* scratch, void* cuda_stream);
+
 /* ------------------------------------------------------------ profiling ----
  * Off by default. flags bit 0: record a CUDA event on the caller's stream between the kernels
  * of each g3d_tdf_batch / g3d_raycast_batch call (bench.py's per-kernel timing);

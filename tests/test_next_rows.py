@@ -65,3 +65,32 @@ def test_raycast_color_gpu_vs_reference(g3d, oracle, golden_dir, tmp_path):
         json.dump({"pose": S.pose_json_payload(0)}, f)
     raytracing.raycast(str(tmp_path / "o.txt"), str(tmp_path / "p.json"), str(tmp_path / "c.png"), str(tmp_path / "d.png"))
     assert (tmp_path / "o.txt").read_bytes() == bytes(z["first_txt"])
+
+
+def test_raymarch_oracle_vs_reference(oracle, golden_dir):
+    z = np.load(os.path.join(golden_dir, "raymarch.npz"))
+    cam = json.loads(str(z["cam"]))["intrinsic"]
+    occ, rgb = oracle.raymarch(z["depth"], z["color"], cam["cx"], cam["cy"], cam["fx"])
+    assert np.array_equal(occ, z["occ"]) and np.array_equal(rgb, z["rgb"])
+
+
+@pytest.mark.gpu
+def test_raymarch_gpu_vs_reference(g3d, oracle, golden_dir, tmp_path):
+    from PIL import Image
+    from generate3d_b200 import raytracing_approach1 as ra
+    z = np.load(os.path.join(golden_dir, "raymarch.npz"))
+    (tmp_path / "cam.json").write_text(str(z["cam"]))
+    Image.fromarray(z["depth"], mode="L").save(tmp_path / "d.png")
+    Image.fromarray(z["color"], mode="RGB").save(tmp_path / "c.png")
+    ra.raycast_to_txt(str(tmp_path / "o.txt"), str(tmp_path / "cam.json"), str(tmp_path / "c.png"), str(tmp_path / "d.png"))
+    assert (tmp_path / "o.txt").read_bytes() == bytes(z["txt"])
+    cam = ra.load_camera(str(tmp_path / "cam.json"))
+    occ, rgb = ra.raymarch(z["depth"], z["color"], cam)
+    assert np.array_equal(occ.cpu().numpy(), z["occ"]) and np.array_equal(rgb.cpu().numpy(), z["rgb"])
+    # a reference-native 512x512 view against the restatement
+    d = S.depth_view(3, 512, 512)
+    c = np.random.default_rng(2).integers(0, 256, (512, 512, 3)).astype(np.uint8)
+    cam2 = ra.Camera(center=(256, 256), focal=(525.0, 525.0), z_near=0.5, z_far=1.5)
+    occ2, rgb2 = ra.raymarch(d, c, cam2)
+    wo, wr = oracle.raymarch(d, c, 256, 256, 525.0)
+    assert np.array_equal(occ2.cpu().numpy(), wo) and np.array_equal(rgb2.cpu().numpy(), wr)
