@@ -8,7 +8,7 @@
 //
 //  1. the u8 depth raster is read ONCE with 16-byte loads and reduced to a
 //     `depth > 0` bit mask in shared memory (H x W/32 words; 8 KB at 256^2),
-//     plus a second mask holding the OR of every 4 consecutive rows;
+//     plus two coarser masks holding the OR of every 4 and every 16 consecutive rows;
 //  2. the corners are shared lattice points, so each of the (dim+1)^3 lattice
 //     points is projected once (7.3x fewer projections) with the reference's
 //     arithmetic: cam = pose @ (g2w @ p) accumulated k = 0..3 with one FMA per
@@ -17,7 +17,7 @@
 //     Planes are projected one at a time and kept two at a time; per plane the
 //     4-corner min/max of every (x, y) cell is formed once with packed 16-bit
 //     SIMD min/max, so a voxel's box is two 8-byte loads and two instructions;
-//  3. each voxel tests its box against the masks 4 rows at a time (half-open,
+//  3. each voxel tests its box against the coarsest fitting mask in at most 4 reads (half-open,
 //     clipped to the image as numpy slicing does); a warp ballots 32 voxels
 //     into one output word, so the bit-packed grid is written without atomics.
 //
@@ -47,8 +47,24 @@ __device__ __forceinline__ int round_clamp(float p, int cmax)
     return (int)r;
 }
 
+// u = (x*f)/|z| + c rounded half-to-even and clamped, as the reference computes it (raytracing.py:71-75), but the
+// IEEE division is only paid when it can matter: a reciprocal-multiply estimate is within a few ulp of the
+// exactly rounded u (rcp_rn 0.5 ulp + one FMA: under 4e-4 px for |u| < 4096), and rint() of the two can only
+// differ when the estimate lies that close to a half-integer. Everything else -- non-finite values, large
+// magnitudes, near-ties (0.2 % of points) -- takes the exact path.
+__device__ __forceinline__ int project_px(float num, float az, float inv_az, float c, int cmax)
+{
+    const float est = fmaf(num, inv_az, c);
+    const float fr = est - floorf(est);
+    if (fabsf(est) < 4096.f && fabsf(fr - 0.5f) > 1e-3f) {
+        const float r = rintf(est);
+        return r <= 0.f ? 0 : (r >= (float)cmax ? cmax : (int)r);
+    }
+    return round_clamp(__fadd_rn(__fdiv_rn(num, az), c), cmax);
+}
+
 template <int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose, int H, int W,
                float focal, float cx, float cy, int clamp_max, int dim, int zs, float inv_dim,
                uint32_t* __restrict__ occ_bits, float* __restrict__ occ_f32,
@@ -62,7 +78,8 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
     const int n = dim + 1, nn = n * n, d2 = dim * dim;
     uint32_t* m1 = smem;                            // [H * Wp]  depth > 0, one bit per pixel
     uint32_t* m4 = m1 + (size_t)H * Wp;             // [H * Wp]  OR of rows r .. r+3
-    uint32_t* lat = m4 + (size_t)H * Wp;            // [2][n*n]  projected lattice plane: u | v << 16
+    uint32_t* m16 = m4 + (size_t)H * Wp;            // [H * Wp]  OR of rows r .. r+15
+    uint32_t* lat = m16 + (size_t)H * Wp;           // [2][n*n]  projected lattice plane: u | v << 16
     uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [2][dim*dim] (min2, max2) of a cell's 4 corners
     const uint8_t* D = depth + (size_t)view * H * W;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -97,6 +114,16 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
             if (row + 3 < H) b |= m1[w + 3 * Wp];
             m4[w] = b;
         }
+    __syncthreads();
+    if (depth)
+        for (int w = tid; w < H * Wp; w += NT) {
+            int row = w / Wp;
+            uint32_t b = m4[w];
+            if (row + 4 < H) b |= m4[w + 4 * Wp];
+            if (row + 8 < H) b |= m4[w + 8 * Wp];
+            if (row + 12 < H) b |= m4[w + 12 * Wp];
+            m16[w] = b;
+        }
 
     // ---- 2. lattice planes are projected once each and kept two at a time
     const float* P = pose + (size_t)view * 16;
@@ -113,10 +140,11 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
             float camx = fmaf(p03, 1.f, fmaf(p02, wz, fmaf(p01, wy, __fmul_rn(p00, wx))));
             float camy = fmaf(p13, 1.f, fmaf(p12, wz, fmaf(p11, wy, __fmul_rn(p10, wx))));
             float camz = fmaf(p23, 1.f, fmaf(p22, wz, fmaf(p21, wy, __fmul_rn(p20, wx))));
-            float az = fabsf(camz);
-            float u = __fadd_rn(__fdiv_rn(__fmul_rn(camx, focal), az), cx);     // raytracing.py:71
-            float v = __fadd_rn(__fdiv_rn(__fmul_rn(-camy, focal), az), cy);    // :70,72
-            out[q] = (uint32_t)round_clamp(u, clamp_max) | ((uint32_t)round_clamp(v, clamp_max) << 16);
+            const float az = fabsf(camz);
+            const float inv_az = __frcp_rn(az);
+            const int u = project_px(__fmul_rn(camx, focal), az, inv_az, cx, clamp_max);     // raytracing.py:71
+            const int v = project_px(__fmul_rn(-camy, focal), az, inv_az, cy, clamp_max);    // :70,72
+            out[q] = (uint32_t)u | ((uint32_t)v << 16);
         }
     };
     auto build_quads = [&](const uint32_t* in, uint2* out) {
@@ -164,27 +192,21 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
                     const int wa = u0 >> 5, wb = (u1 - 1) >> 5;
                     const uint32_t ma = 0xffffffffu << (u0 & 31);
                     const uint32_t mb = 0xffffffffu >> (31 - ((u1 - 1) & 31));
-                    int row = v0;
-                    if (wa == wb) {                 // the usual case: the box spans one mask word
-                        const uint32_t mm = ma & mb;
-                        uint32_t hit = 0;
-                        for (; row + 4 <= v1; row += 4) hit |= m4[row * Wp + wa];
-                        for (; row < v1; ++row) hit |= m1[row * Wp + wa];
-                        occ = (hit & mm) != 0;
-                    } else {
-                        uint32_t hit = 0;
-                        for (; row + 4 <= v1; row += 4) {
-                            const uint32_t* mr = m4 + row * Wp;
-                            hit |= (mr[wa] & ma) | (mr[wb] & mb);
-                            for (int w = wa + 1; w < wb; ++w) hit |= mr[w];
-                        }
-                        for (; row < v1; ++row) {
-                            const uint32_t* mr = m1 + row * Wp;
-                            hit |= (mr[wa] & ma) | (mr[wb] & mb);
-                            for (int w = wa + 1; w < wb; ++w) hit |= mr[w];
-                        }
-                        occ = hit != 0;
+                    // rows [v0, v1) are covered by at most four reads of the coarsest fitting mask: windows of
+                    // h rows starting at v0, v0+h, ... and one ending at v1 (overlap is harmless for an OR)
+                    const int nrow = v1 - v0;
+                    const uint32_t* mk = nrow >= 16 ? m16 : (nrow >= 4 ? m4 : m1);
+                    const int h = nrow >= 16 ? 16 : (nrow >= 4 ? 4 : 1);
+                    uint32_t hit = 0;
+                    for (int w = wa; w <= wb; ++w) {
+                        uint32_t acc = 0;
+                        for (int row = v0; row + h <= v1; row += h) acc |= mk[row * Wp + w];
+                        acc |= mk[(v1 - h) * Wp + w];
+                        if (w == wa) acc &= ma;
+                        if (w == wb) acc &= mb;
+                        hit |= acc;
                     }
+                    occ = hit != 0;
                 }
                 if (occ_f32) occ_f32[(long long)view * nvox + lin] = occ ? 1.f : 0.f;
             }
@@ -212,7 +234,7 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     if (!pose || (!depth && (occ_bits || occ_f32))) { set_error("raycast: null input"); return G3D_ERR_INVALID; }
     constexpr int NT = 512;
     const int n = dim + 1;
-    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 2 + ((size_t)2 * n * n + 1) * 4 + (size_t)2 * dim * dim * 8;
+    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 3 + ((size_t)2 * n * n + 1) * 4 + (size_t)2 * dim * dim * 8;
     if (smem > 227 * 1024) {
         set_error("raycast: image %dx%d needs %zu bytes of shared memory (max 232448)", H, W, smem);
         return G3D_ERR_INVALID;
