@@ -148,14 +148,18 @@ def raycast_depth(txt_file, pose_file, depth_file):
 
 
 def generate_raycasted_model(synset_id, model_id, renderings_root="/media/sda2/shapenet/shapenet-renderings/",
-                             out_root="/media/sda2/shapenet/shapenet-raytraced/"):
-    """raytracing.py:147-166 (the cube-per-voxel .ply visualisation is out of scope)."""
+                             out_root="/media/sda2/shapenet/shapenet-raytraced/", write_ply=True):
+    """raytracing.py:147-166: view 00 of a rendered model -> <out_root>/<synset>/<model>.txt (+ the cube PLY)."""
+    from .voxel_grid import txt_to_mesh
     outdir = os.path.join(out_root, synset_id)
     pathlib.Path(outdir).mkdir(parents=True, exist_ok=True)
     base = os.path.join(renderings_root, synset_id, model_id)
+    voxel_file = os.path.join(outdir, model_id + ".ply")
     voxel_txt_file = os.path.join(outdir, model_id + ".txt")
-    if os.path.exists(voxel_txt_file):
+    if os.path.exists(voxel_txt_file) and (os.path.exists(voxel_file) or not write_ply):
         print(synset_id, " : ", model_id, " already exists. Skipping......")
         return
     raycast_depth(voxel_txt_file, os.path.join(base, "pose", "pose00.json"),
                   os.path.join(base, "depth", "depth00.png"))
+    if write_ply:
+        txt_to_mesh(voxel_txt_file, voxel_file)

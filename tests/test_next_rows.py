@@ -94,3 +94,12 @@ def test_raymarch_gpu_vs_reference(g3d, oracle, golden_dir, tmp_path):
     occ2, rgb2 = ra.raymarch(d, c, cam2)
     wo, wr = oracle.raymarch(d, c, 256, 256, 525.0)
     assert np.array_equal(occ2.cpu().numpy(), wo) and np.array_equal(rgb2.cpu().numpy(), wr)
+
+
+def test_txt_to_mesh_ply_bytes(golden_dir, tmp_path):
+    """voxel_grid.txt_to_mesh: the cube-per-voxel PLY is byte-identical to the reference's."""
+    from generate3d_b200 import voxel_grid
+    z = np.load(os.path.join(golden_dir, "ply.npz"))
+    (tmp_path / "g.txt").write_bytes(bytes(z["txt"]))
+    voxel_grid.txt_to_mesh(str(tmp_path / "g.txt"), str(tmp_path / "g.ply"))
+    assert (tmp_path / "g.ply").read_bytes() == bytes(z["ply"])
