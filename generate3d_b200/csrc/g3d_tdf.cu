@@ -442,24 +442,51 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
 {
     u64 n_eval = 0;
     extern __shared__ uint32_t s_mem[];
-    __shared__ int s_prev[16][8];
+    // s_thr[s][r][cls]: code of the last sweep before s in which a node of boundary class cls examined the
+    // neighbour that slot r of sweep s points at (-1: never). cls = cx + 3*cy + 9*cz, c = 0 at coordinate 0,
+    // 2 at coordinate n-1, 1 in between: a node on a grid face is not part of every sweep's lattice.
+    __shared__ int8_t s_thr[16][7][27];
+    __shared__ int s_tmin[16];                      // smallest s_thr over the slots and the classes present in sweep s
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* q_tri = s_mem + lev_words + warp * (3 * kSweepQueue);
     uint32_t* q_pos = q_tri + kSweepQueue;
     float* q_res = reinterpret_cast<float*>(q_pos + kSweepQueue);
+    // s_dirty[d][L]: newest change code among the upwind neighbours of the nodes of level L in direction d
+    uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (3 * kSweepQueue));   // [8][nlev]
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
-    if (threadIdx.x < 16 * 8) {
-        // slot r+1 = (ai, aj, ak) bit mask of the axes on which the neighbour is one step upwind
-        const int s = threadIdx.x >> 3, r = threadIdx.x & 7, a = r + 1;
-        int di, dj, dk, thr = -1;
-        sweep_dir(s, di, dj, dk);
+    for (int l = threadIdx.x; l < 8 * nlev; l += NT) s_dirty[l] = 0;
+    for (int e = threadIdx.x; e < 16 * 7 * 27; e += NT) {
+        const int cls = e % 27, r = (e / 27) % 7, s = e / (27 * 7), a = r + 1;
+        const int c3[3] = { cls % 3, (cls / 3) % 3, cls / 9 };
+        int d[3], thr = -1;
+        sweep_dir(s, d[0], d[1], d[2]);
         for (int sp = 0; sp < s; ++sp) {
-            int ei, ej, ek;
-            sweep_dir(sp, ei, ej, ek);
-            if ((!(a & 1) || ei == di) && (!(a & 2) || ej == dj) && (!(a & 4) || ek == dk)) thr = sp + 1;
+            int e3[3];
+            sweep_dir(sp, e3[0], e3[1], e3[2]);
+            bool ok = true;
+            for (int ax = 0; ax < 3; ++ax) {
+                if (((a >> ax) & 1) && e3[ax] != d[ax]) ok = false;            // same neighbour upwind
+                if (e3[ax] > 0 ? c3[ax] == 0 : c3[ax] == 2) ok = false;        // the node was swept at all
+            }
+            if (ok) thr = sp + 1;
         }
-        s_prev[s][r] = thr;                         // examine nb iff chg[nb] > thr
+        s_thr[s][r][cls] = (int8_t)thr;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int s = threadIdx.x;
+        int d[3], m = 127;
+        sweep_dir(s, d[0], d[1], d[2]);
+        for (int cls = 0; cls < 27; ++cls) {
+            const int c3[3] = { cls % 3, (cls / 3) % 3, cls / 9 };
+            bool present = true;
+            for (int ax = 0; ax < 3; ++ax)
+                if (d[ax] > 0 ? c3[ax] == 0 : c3[ax] == 2) present = false;
+            if (present)
+                for (int r = 0; r < 7; ++r) m = min(m, (int)s_thr[s][r][cls]);
+        }
+        s_tmin[s] = m;
     }
     __syncthreads();
     const int csize = CL ? (int)cluster_nctarank() : 1, crank = CL ? (int)cluster_ctarank() : 0;
@@ -476,9 +503,12 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
         int di, dj, dk;
         sweep_dir(s, di, dj, dk);
         const int oi = di, oj = dj * sj, ok = dk * sk;
-        const int t0 = s_prev[s][0], t1 = s_prev[s][1], t2 = s_prev[s][2], t3 = s_prev[s][3], t4 = s_prev[s][4],
-                  t5 = s_prev[s][5], t6 = s_prev[s][6];
+        const int tmin = s_tmin[s];
+        const uint8_t* dirty = s_dirty + (s & 7) * nlev;
         for (int L = 0; L < nlev; ++L) {
+            // nothing upwind of this whole level has changed since it was last examined: every comparison the
+            // reference would make here is known to fail. (Cluster variant: the table is per CTA, no skipping.)
+            if (!CL && (int)dirty[L] <= tmin) continue;
             const int beg = s_lev[L], end = s_lev[L + 1];
             for (int qb = beg + crank * NT + warp * 32; qb < end; qb += NT * csize) {
                 const int q = qb + lane;
@@ -496,12 +526,13 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
                     // the 7 upwind neighbours in the order of cpp:72-78
                     const int n0 = n - oi, n1 = n - oj, n2 = n - oi - oj, n3 = n - ok, n4 = n - oi - ok,
                               n5 = n - oj - ok, n6 = n - oi - oj - ok;
-                    const bool interior = i > 0 && i < ni - 1 && j > 0 && j < nj - 1 && k > 0 && k < nk - 1;
-                    uint32_t look = 127u;
-                    if (interior)
-                        look = ((int)G[n0] > t0 ? 1u : 0u) | ((int)G[n1] > t1 ? 2u : 0u) | ((int)G[n2] > t2 ? 4u : 0u) |
-                               ((int)G[n3] > t3 ? 8u : 0u) | ((int)G[n4] > t4 ? 16u : 0u) | ((int)G[n5] > t5 ? 32u : 0u) |
-                               ((int)G[n6] > t6 ? 64u : 0u);
+                    const int cls = (i == 0 ? 0 : (i == ni - 1 ? 2 : 1)) + 3 * (j == 0 ? 0 : (j == nj - 1 ? 2 : 1)) +
+                                    9 * (k == 0 ? 0 : (k == nk - 1 ? 2 : 1));
+                    const int8_t* th = &s_thr[s][0][cls];
+                    const uint32_t look =
+                        ((int)G[n0] > th[0] ? 1u : 0u) | ((int)G[n1] > th[27] ? 2u : 0u) | ((int)G[n2] > th[54] ? 4u : 0u) |
+                        ((int)G[n3] > th[81] ? 8u : 0u) | ((int)G[n4] > th[108] ? 16u : 0u) | ((int)G[n5] > th[135] ? 32u : 0u) |
+                        ((int)G[n6] > th[162] ? 64u : 0u);
                     if (look) {
                         if (look & 1u) c0 = Klo[2 * n0];
                         if (look & 2u) c1 = Klo[2 * n1];
@@ -571,8 +602,27 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
                     if (need & 32u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c5; changed = true; } }
                     if (need & 64u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c6; changed = true; } }
                     if (changed) {
+                        const uint8_t code = (uint8_t)(s + 1);
                         K[n] = ((u64)__float_as_uint(phi) << 32) | (uint32_t)ct;
-                        G[n] = (uint8_t)(s + 1);
+                        G[n] = code;
+                        if (!CL) {
+                            // in every direction d this node is upwind of nodes 1..3 levels further on: stamp those
+                            // levels (codes only grow and all writers of a sweep write the same value)
+                            const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
+#pragma unroll
+                            for (int dq = 0; dq < 8; ++dq) {
+                                int ei, ej, ek;
+                                sweep_dir(dq, ei, ej, ek);
+                                const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) +
+                                               (ek > 0 ? pk - 1 : nk - 2 - pk);
+                                uint8_t* row = s_dirty + dq * nlev;
+#pragma unroll
+                                for (int up = 1; up <= 3; ++up) {
+                                    const int l = lv + up;
+                                    if (l >= 0 && l < nlev) row[l] = code;
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -681,7 +731,7 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
                     u64* cnt, cudaStream_t stream)
 {
     const int lev_words = (nlev + 1 + 3) & ~3;
-    const size_t smem = (size_t)(lev_words + (NT / 32) * 3 * kSweepQueue) * 4;
+    const size_t smem = (size_t)(lev_words + (NT / 32) * 3 * kSweepQueue) * 4 + (size_t)8 * nlev;
     auto kern = tdf_sweep_kernel<NT, CL>;
     G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
