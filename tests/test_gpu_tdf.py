@@ -336,3 +336,30 @@ def test_faithful_single_huge_triangle_and_outside_mesh(g3d, oracle):
         phi, ct = dfgen.make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32, return_closest_tri=True)
         assert np.array_equal(_bits(phi.cpu().numpy()), _bits(want["phi"]))
         assert np.array_equal(ct.cpu().numpy(), want["closest_tri"])
+
+
+def test_host_abi_chunked_path_equals_device_abi(g3d):
+    """>= 64 meshes: the host front end stages triangles in 4 chunks on a copy stream; results must equal the
+    one-shot device API bit for bit (faithful and exact)."""
+    from generate3d_b200 import dfgen
+    V, voff, T, toff = S.table_batch(70, 3, first_seed=300)
+    L = g3d.lib()
+    ctx = C.c_void_p()
+    g3d.check(L.g3d_context_create(0, C.byref(ctx)))
+    for mode in (0, 1):
+        p = g3d.TdfParams()
+        g2w = np.zeros(16, np.float32)
+        g3d.check(L.g3d_dfgen_geometry(32, 0, 1, None, None, C.byref(p), g2w.ctypes.data))
+        p.trunc, p.occ_thresh, p.mode = 3.0, 1.0, mode
+        sdf = np.empty((70, 32, 32, 32), np.float32)
+        ct = np.empty((70, 32, 32, 32), np.int32)
+        status = np.empty(70, np.int32)
+        o = g3d.TdfOutputs()
+        o.sdf, o.closest_tri, o.status = sdf.ctypes.data, ct.ctypes.data, status.ctypes.data
+        g3d.check(L.g3d_tdf_batch_host(ctx, V.ctypes.data, voff.ctypes.data, T.ctypes.data, toff.ctypes.data, 70,
+                                       C.byref(p), C.byref(o)))
+        r = dfgen.tdf_batch(V, voff, T, toff, mode="faithful" if mode == 0 else "exact", outputs=("sdf", "closest_tri", "status"))
+        assert not status.any()
+        assert np.array_equal(_bits(sdf), _bits(r["sdf"].cpu().numpy()))
+        assert np.array_equal(ct, r["closest_tri"].cpu().numpy())
+    L.g3d_context_destroy(ctx)
