@@ -101,6 +101,8 @@ __device__ __forceinline__ V3 node_pos(int i, int j, int k, const g3d_tdf_params
 
 #include "g3d_tdf_exact.cuh"
 
+using exact::prefetch_l1;
+
 // ------------------------------------------------------------------ prep ----
 __device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
@@ -301,6 +303,10 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
     int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t nvox = nvox_of(P);
     for (int64_t t = t_first + warp; t < total_tris; t += nwarp) {
+        if (lane < 2 && t + nwarp < total_tris) {    // the next triangle's box and record are two dependent loads away
+            if (lane == 0) prefetch_l1(box + t + nwarp);
+            else prefetch_l1(tri + 4 * (t + nwarp));
+        }
         int4 b = __ldg(box + t);
         int i0 = b.x & 0xffff, i1 = b.x >> 16, j0 = b.y & 0xffff, j1 = b.y >> 16, k0 = b.z & 0xffff, k1 = b.z >> 16;
         int bi = i1 - i0 + 1, bj = j1 - j0 + 1, bk = k1 - k0 + 1;
@@ -413,8 +419,6 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 //      pushes them into a private shared-memory queue, evaluates the queue densely (one pair
 //      per lane), and the owners then replay the results in neighbour order.
 constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
-
-using exact::prefetch_l1;
 
 __device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
 {
