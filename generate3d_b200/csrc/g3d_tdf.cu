@@ -1,35 +1,34 @@
-// g3d_tdf.cu -- reference-faithful distance field on sm_100a.
+// g3d_tdf.cu -- the distance-field path on sm_100a (both modes), behind g3d_tdf_batch.
 //
-// Reproduces make_level_set3 (src/dfgen/makelevelset3.cpp:118-183) bit for bit,
-// for a batch of meshes, with the sequential loops re-expressed as
-// order-independent parallel steps:
+// Faithful mode reproduces make_level_set3 (src/dfgen/makelevelset3.cpp:118-183) bit for bit -- phi AND
+// closest_tri -- for a batch of meshes, with the reference's sequential loops re-expressed as
+// order-independent parallel steps and with every evaluation skipped that provably cannot change the result:
 //
-//  tdf_prep      one thread / triangle: gathers the three vertices into a
-//                64-byte record (vertices + the per-triangle invariants of the
-//                distance function), computes the double-precision grid coordinates,
-//                the band box [int(min)-b, int(max)+b+1] (cpp:131-137) and the
-//                x-ray intersection counts (cpp:147-160). Only the PARITY of the
-//                counts is ever used (cpp:178), so they are kept as XOR-ed bits.
-//  tdf_init      one warp / triangle over its band box. The reference's serial
-//                "if (d < phi) {phi = d; closest = t}" over t = 0..T-1 ends at
-//                (min d, lowest t attaining it); atomicMin on the 64-bit key
-//                (float_bits(d) << 32 | t) is exactly that, in any order.
-//  tdf_sweep     one CTA / mesh, the 2 x 8 Gauss-Seidel sweeps (cpp:57-80,
-//                163-172). Within one sweep node (a,b,c) (sweep-relative) reads
-//                only nodes of smaller a+b+c, so the nodes of one anti-diagonal
-//                level are independent: 16 x (ni+nj+nk-5) block-synchronous
-//                wavefront steps instead of 16 x (n-1)^3 serial ones. Each node
-//                re-tests its 7 upwind neighbours in the reference's order
-//                with strict <.
-//  tdf_finalize  one warp / grid row: running parity along i (cpp:174-182),
-//                x out_scale (main.cpp:119), and the fused epilogues the
-//                pipeline applies later on the CPU: |sdf| <= 1 occupancy
-//                (vox2mesh/main.cpp:92), clamp at trunc (dataset_loader.py:
-//                137-139), sign*log(|x|+1) (losses.py:7-11).
+//  tdf_prep      one thread / triangle: gathers the three vertices into a 64-byte record (vertices + the
+//                per-triangle invariants of the distance function, computed with the reference's rounded
+//                operation order), the double-precision grid coordinates, the band box
+//                [int(min)-b, int(max)+b+1] (cpp:131-137) and the x-ray intersection counts (cpp:147-160).
+//                Only the PARITY of the counts is ever used (cpp:178), so they are kept as XOR-ed bits.
+//  tdf_init      one warp / triangle over its band box. The reference's serial "if (d < phi) {phi = d;
+//                closest = t}" over t = 0..T-1 ends at (min d, lowest t attaining it); atomicMin on the 64-bit
+//                key (float_bits(d) << 32 | t) is exactly that, in any order. A node farther from the
+//                triangle's bounding box than its current phi cannot win and is dropped before the evaluation
+//                (9 in 10 are); survivors are compacted and evaluated 32 at a time.
+//  tdf_sweep     one CTA (or one thread-block cluster) / mesh, the 2 x 8 Gauss-Seidel sweeps (cpp:57-80,
+//                163-172). Within one sweep node (a,b,c) (sweep-relative) reads only nodes of smaller a+b+c,
+//                so the nodes of one anti-diagonal level are independent: 16 x (ni+nj+nk-5) synchronous
+//                wavefront steps instead of 16 x (n-1)^3 serial ones. See the kernel for the three exact
+//                shortcuts (duplicate candidates, unchanged neighbours, untouched levels).
+//  tdf_finalize  one warp / grid row: running parity along i (cpp:174-182), x out_scale (main.cpp:119), and
+//                the fused epilogues the pipeline applies later on the CPU: |sdf| <= 1 occupancy
+//                (vox2mesh/main.cpp:92), clamp at trunc (dataset_loader.py:137-139), sign*log(|x|+1)
+//                (losses.py:7-11).
 //
-// HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B;
-// keys u64 [n_mesh, nk, nj, ni] (hi = phi bits, lo = closest_tri); parity bits
-// u32 [n_mesh, ceil(nvox/32)]; sweep order table (shared by all meshes).
+// Exact mode (g3d_tdf_exact.cuh) shares prep and finalize and replaces init + sweeps by a culled brute force.
+//
+// HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B; keys u64 [n_mesh, nk, nj, ni]
+// (hi = phi bits, lo = closest_tri); change bytes u8 [n_mesh, nvox]; parity bits u32 [n_mesh, ceil(nvox/32)];
+// sweep order table (shared by all meshes).
 #include <limits.h>
 #include <stdlib.h>
 
