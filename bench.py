@@ -271,6 +271,10 @@ def run_b200(args, rank, world, local):
     if tt and M == 1024 and args.n == 18:
         roofline["traffic"] = tt["bytes_per_launch"]
         roofline["traffic_source"] = tt["source"] + " (ncu --set full, same workload)"
+        if dom_ms:
+            # the other roofline of the same kernel: measured DRAM traffic over the live kernel time
+            roofline["dram_gbs"] = tt["bytes_per_launch"] / (dom_ms * 1e-3) / 1e9
+            roofline["dram_frac_of_hbm_peak"] = roofline["dram_gbs"] / peaks["hbm_gbs"]
 
     # ---- the other TDF mode, same batch, fewer steps: rides along under "other_mode"
     other = "exact" if args.mode == "faithful" else "faithful"
