@@ -165,7 +165,9 @@ int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_ver
     if (rc != G3D_OK) return rc;
     rc = tdf_stage_tris(verts, vert_off, tris, tri_off, 0, total_tris, total_tris, n_mesh, *params, *out, workspace, s);
     if (rc != G3D_OK) return rc;
-    return tdf_finish(vert_off, tri_off, total_tris, n_mesh, *params, *out, workspace, s);
+    rc = tdf_solve(tri_off, total_tris, n_mesh, *params, workspace, s);
+    if (rc != G3D_OK) return rc;
+    return tdf_finalize(vert_off, tri_off, total_tris, n_mesh, 0, n_mesh, *params, *out, workspace, s);
 }
 
 int g3d_tdf_from_sdf(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog, void* cuda_stream)
@@ -347,16 +349,27 @@ int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_o
         rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], nt, n_mesh, *params, d, ws, s);
         if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
     }
-    rc = tdf_finish(dvo, dto, nt, n_mesh, *params, d, ws, s);
+    rc = tdf_solve(dto, nt, n_mesh, *params, ws, s);
     if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
-    const size_t gb = (size_t)n_mesh * nvox * 4;
-    if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf, d.sdf, gb, cudaMemcpyDeviceToHost, s));
-    if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf, d.tdf, gb, cudaMemcpyDeviceToHost, s));
-    if (out->tdflog) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdflog, d.tdflog, gb, cudaMemcpyDeviceToHost, s));
-    if (out->occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_bits, d.occ_bits, (size_t)n_mesh * pw * 4, cudaMemcpyDeviceToHost, s));
-    if (out->occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_f32, d.occ_f32, gb, cudaMemcpyDeviceToHost, s));
-    if (out->closest_tri) G3D_CUDA_TRY(cudaMemcpyAsync(out->closest_tri, d.closest_tri, gb, cudaMemcpyDeviceToHost, s));
+    // The epilogue runs per chunk of meshes and each chunk's results start their way back (on the copy stream,
+    // idle by now) while the next chunk is still being finalised.
+    const size_t gv = (size_t)nvox;
+    for (int ch = 0; ch < nch; ++ch) {
+        const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch), nm = m1 - m0;
+        rc = tdf_finalize(dvo, dto, nt, n_mesh, m0, m1, *params, d, ws, s);
+        if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
+        G3D_CUDA_TRY(cudaEventRecord(c->ev_in[ch], s));
+        G3D_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_in[ch], 0));
+        const size_t gb = (size_t)nm * gv * 4, go = (size_t)m0 * gv;
+        if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf + go, d.sdf + go, gb, cudaMemcpyDeviceToHost, c->s_in));
+        if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf + go, d.tdf + go, gb, cudaMemcpyDeviceToHost, c->s_in));
+        if (out->tdflog) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdflog + go, d.tdflog + go, gb, cudaMemcpyDeviceToHost, c->s_in));
+        if (out->occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_bits + (size_t)m0 * pw, d.occ_bits + (size_t)m0 * pw, (size_t)nm * pw * 4, cudaMemcpyDeviceToHost, c->s_in));
+        if (out->occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_f32 + go, d.occ_f32 + go, gb, cudaMemcpyDeviceToHost, c->s_in));
+        if (out->closest_tri) G3D_CUDA_TRY(cudaMemcpyAsync(out->closest_tri + go, d.closest_tri + go, gb, cudaMemcpyDeviceToHost, c->s_in));
+    }
     if (out->status) G3D_CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, s));
+    G3D_CUDA_TRY(cudaStreamSynchronize(c->s_in));
     G3D_CUDA_TRY(cudaStreamSynchronize(s));
     return G3D_OK;
 }

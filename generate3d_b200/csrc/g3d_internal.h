@@ -19,15 +19,17 @@ int  cuda_fail(cudaError_t e, const char* what);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// ---- TDF, both modes (g3d_tdf.cu), in three phases (see the definitions)
+// ---- TDF, both modes (g3d_tdf.cu), in four phases (see the definitions)
 size_t tdf_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
 int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
               const g3d_tdf_outputs& out, void* ws, size_t ws_bytes, cudaStream_t stream);
 int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* tris, const int64_t* tri_off,
                    int64_t t0, int64_t t1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
                    const g3d_tdf_outputs& out, void* ws, cudaStream_t stream);
-int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tris, int32_t n_mesh,
-               const g3d_tdf_params& p, const g3d_tdf_outputs& out, void* ws, cudaStream_t stream);
+int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p, void* ws,
+              cudaStream_t stream);
+int tdf_finalize(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, int32_t m0,
+                 int32_t m1, const g3d_tdf_params& p, const g3d_tdf_outputs& out, void* ws, cudaStream_t stream);
 
 int tdf_from_sdf_launch(const float* sdf, int64_t n, float trunc, float* tdf, float* tdflog,
                         cudaStream_t stream);

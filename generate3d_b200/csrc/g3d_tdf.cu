@@ -645,13 +645,14 @@ __device__ __forceinline__ float log_transform(float x)
 
 __global__ void __launch_bounds__(256)
 tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ parity,
-                    const int64_t* __restrict__ vert_off, const int64_t* __restrict__ tri_off, int n_mesh,
+                    const int64_t* __restrict__ vert_off, const int64_t* __restrict__ tri_off, int mesh0, int n_mesh,
                     g3d_tdf_params P, g3d_tdf_outputs O, int signed_mode)
 {
     const int lane = threadIdx.x & 31;
-    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (mesh, k, j)
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (mesh - mesh0, k, j)
     int64_t nrow = (int64_t)n_mesh * P.nk * P.nj;
     if (row >= nrow) return;
+    row += (int64_t)mesh0 * P.nk * P.nj;
     int mesh = (int)(row / ((int64_t)P.nk * P.nj));
     int64_t nvox = nvox_of(P), pw = (nvox + 31) / 32;
     int64_t rbase = (row - (int64_t)mesh * P.nk * P.nj) * P.ni;           // node index of i = 0
@@ -800,11 +801,12 @@ int tdf_validate(int32_t n_mesh, int64_t total_verts, int64_t total_tris, const 
     return G3D_OK;
 }
 
-// The work of one batch call in three phases, so that the host-buffer front end can start on the first
+// The work of one batch call in four phases, so that the host-buffer front end can start on the first
 // triangles while the rest of the batch is still crossing PCIe:
 //   tdf_begin        validate, carve the workspace, initialise keys / parity / change bytes
 //   tdf_stage_tris   per-triangle work for triangles [t0, t1): records, boxes, parity (+ band init, faithful mode)
-//   tdf_finish       the whole-batch part: sweeps or the exact kernel, then the fused epilogue
+//   tdf_solve        the whole-batch part: sweeps, or the exact kernel
+//   tdf_finalize     the fused epilogue for meshes [m0, m1), so that results can start their way back per chunk
 int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
               const g3d_tdf_outputs& out, void* ws, size_t ws_bytes, cudaStream_t stream)
 {
@@ -870,15 +872,13 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* 
     return G3D_OK;
 }
 
-int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tris, int32_t n_mesh,
-               const g3d_tdf_params& p, const g3d_tdf_outputs& out, void* ws, cudaStream_t stream)
+int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p, void* ws,
+              cudaStream_t stream)
 {
     if (n_mesh == 0) return G3D_OK;
     u64* cnt = prof_counters();
-    const u64* key; const uint32_t* parity;
     if (p.mode == G3D_MODE_EXACT) {
         exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
-        key = w.key; parity = w.parity;
         if (total_tris > 0) {
             constexpr int WX = exact::kWX, WY = exact::kWY, WZ = exact::kWZ, NT = WX * WY * WZ * 32, TILE = exact::kTile;
             const int nbx = (p.ni + WX * 4 - 1) / (WX * 4), nby = (p.nj + WY * 4 - 1) / (WY * 4), nbz = (p.nk + WZ * 2 - 1) / (WZ * 2);
@@ -913,7 +913,6 @@ int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tr
         }
     } else {
         TdfWs w = carve(ws, n_mesh, total_tris, p);
-        key = w.key; parity = w.parity;
         const int nlev = nlev_of(p);
         if (total_tris > 0 && nlev > 0) {
             size_t smem = (size_t)(nlev + 1) * 4;
@@ -924,8 +923,20 @@ int tdf_finish(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tr
             prof_mark(ST_SWEEP, stream);
         }
     }
-    tdf_finalize_kernel<<<(unsigned)(((int64_t)n_mesh * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
-        key, parity, vert_off, tri_off, n_mesh, p, out, 1);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+// fused epilogue for meshes [m0, m1): signs, scaling, occupancy, truncation, log transform, all outputs
+int tdf_finalize(const int64_t* vert_off, const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, int32_t m0,
+                 int32_t m1, const g3d_tdf_params& p, const g3d_tdf_outputs& out, void* ws, cudaStream_t stream)
+{
+    if (n_mesh == 0 || m1 <= m0) return G3D_OK;
+    const u64* key; const uint32_t* parity;
+    if (p.mode == G3D_MODE_EXACT) { exact::Ws w = exact::carve(ws, n_mesh, total_tris, p); key = w.key; parity = w.parity; }
+    else { TdfWs w = carve(ws, n_mesh, total_tris, p); key = w.key; parity = w.parity; }
+    tdf_finalize_kernel<<<(unsigned)(((int64_t)(m1 - m0) * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
+        key, parity, vert_off, tri_off, m0, m1 - m0, p, out, 1);
     prof_mark(ST_FINAL, stream);
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
