@@ -903,7 +903,7 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
                     S = fmaxf(S, fabsf(p.origin[a]));
                     S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
                 }
-                const float eta = 2e-4f * S, kappa = 1e-6f * S * S;
+                const float eta = 0.f, kappa = 1e-10f * S * S;
                 const size_t smem = (size_t)3 * TILE * 32 + (size_t)2 * TILE * 4 + 3 * 8 + 4 * 4 + (size_t)(NT / 32) * 4 + (size_t)(NT / 32) * 64 * 4;
                 G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 exact::tdf_exact2_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(

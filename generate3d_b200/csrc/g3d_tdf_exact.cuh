@@ -121,7 +121,9 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
         inside = cnt & 1;
     }
     const V3 gx = node_pos(i, j, k, P);
-    float best = valid ? (inside ? __int_as_float(0x7f800000) : R) : 0.f;
+    // like the reference's phi, the running minimum starts at `far` (makelevelset3.cpp:123): a triangle farther
+    // away than that never registers. Outside voxels may stop at the truncation radius instead.
+    float best = valid ? (inside ? far : fminf(R, far)) : 0.f;
     uint32_t best_t = 0xffffffffu;
 
     // boxes of the brick and of the block (node positions are monotone in the index)
@@ -130,7 +132,7 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
     const V3 blk_lo = node_pos(cbx * BX, cby * BY, cbz * BZ, P);
     const V3 blk_hi = node_pos(min(cbx * BX + BX - 1, ni - 1), min(cby * BY + BY - 1, nj - 1), min(cbz * BZ + BZ - 1, nk - 1), P);
     const int any_inside = __syncthreads_or(inside ? 1 : 0);
-    const float blk_bound2 = any_inside ? __int_as_float(0x7f800000) : bound2_of(R);
+    const float blk_bound2 = bound2_of(any_inside ? far : fminf(R, far));
 
     const int64_t t0 = tri_off[mesh];
     const int T = (int)(tri_off[mesh + 1] - t0);
@@ -204,7 +206,7 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
                 m &= m - 1;
                 const uint32_t t = __shfl_sync(0xffffffffu, tq, src);
                 const float d = point_triangle_distance(gx, load_trirec(Tm + 4 * (int64_t)t));
-                if (d < best || (d == best && t < best_t)) { best = d; best_t = t; }
+                if (d < best || (d == best && best_t != 0xffffffffu && t < best_t)) { best = d; best_t = t; }
                 n_pairs += valid ? 1 : 0;
             }
         }
@@ -228,13 +230,19 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
 // can be the minimum of the reference's float function; those few are queued and re-evaluated 32
 // at a time with the bit-faithful function (stage 2), which alone decides the result.
 //
-// Why this is still exact: let d*(t) be the faithful float distance and a(t) the cheap one, with
-// |a(t) - d*(t)| <= e for every non-flagged triangle. If t0 minimises d*, then for every t,
-// a(t) >= d*(t) - e >= d*(t0) - e >= a(t0) - 2e, so a(t0) <= min_t a(t) + 2e: t0 passes the filter
-// "a <= running min + margin" whenever margin >= 2e (the running min only decreases). The margin
-// used is 2e-4 * S absolute (S = extent of the coordinates) plus 0.1 %, about 1000x the observed
-// discrepancy. Triangles for which no such e holds -- slivers (sin^2 < 0.001, where the cheap rating could be off by more than ~6e-5 relative), zero-length edges,
-// non-finite vertices -- are flagged at record-build time and always go to stage 2.
+// Why this is still exact: stage 1 works on intervals. For every non-flagged triangle the cheap squared
+// distance a2 comes with an error bound e2 = 2e-6 * (|x0-x3|^2 + the three squared edge lengths): every
+// intermediate of the rating is bounded by that sum and fewer than twenty roundings of 2^-24 relative size are
+// involved, and the closest point is formed explicitly (x3 + w23 x13 + w31 x23) so that the error of the
+// barycentric solve enters only to second order (slivers with sin^2 < 0.001 are flagged instead). So
+// a2 - e2 <= d^2 <= a2 + e2 for the true distance d, and the reference's float function f agrees with d to
+// about 1e-7 relative (measured; its own closest-point construction has the same second-order property).
+// A voxel keeps ub2 = min_t (a2 + e2), an upper bound of min_t d^2, and a triangle goes to stage 2 iff
+// a2 - e2 <= 1.002 * ub2 + kappa. The minimiser t0 of f always does: d(t0) <= f(t0)(1+1e-6) <= f(t)(1+1e-6)
+// <= d(t)(1+2e-6) for every t, hence a2(t0) - e2(t0) <= d(t0)^2 <= 1.00001 * ub2. kappa (1e-10 * S^2, S the
+// extent of the coordinates) covers distances so small that f's absolute rounding dominates. Triangles for which
+// no such bound holds -- slivers, zero-length edges, non-finite vertices -- are flagged at record-build time and
+// always go to stage 2.
 struct FastRec {                                     // 5 x float4 = 80 B
     float4 f0;   // x3.xyz, invdet (NaN = always evaluate faithfully)
     float4 f1;   // x13.xyz, m13
@@ -262,8 +270,9 @@ __device__ __forceinline__ void store_fastrec(float4* p, V3 x1, V3 x2, V3 x3)
     p[4] = make_float4(d, 1.f / m13, 1.f / m23, 1.f / m12);
 }
 
-// cheap squared point-triangle distance; `flagged` is set for records that must go to stage 2
-__device__ __forceinline__ float fast_dist2(V3 x0, const float4* __restrict__ p, bool& flagged)
+// cheap squared point-triangle distance a2 and its error bound e2; `flagged` is set for records that must go
+// to stage 2 unconditionally
+__device__ __forceinline__ float fast_dist2(V3 x0, const float4* __restrict__ p, bool& flagged, float& e2)
 {
     const float4 f0 = __ldg(p), f1 = __ldg(p + 1), f2 = __ldg(p + 2), f3 = __ldg(p + 3), f4 = __ldg(p + 4);
     flagged = !(f0.w == f0.w);
@@ -274,17 +283,23 @@ __device__ __forceinline__ float fast_dist2(V3 x0, const float4* __restrict__ p,
     const float w23 = f0.w * fmaf(-f4.x, b, f2.w * a);
     const float w31 = f0.w * fmaf(-f4.x, a, f1.w * b);
     const float w12 = 1.f - w23 - w31;
-    const float plane = vv - fmaf(w31, b, w23 * a);
+    // x0 minus its projection onto the plane, formed explicitly: errors of w23 / w31 move the foot point inside
+    // the plane only, which changes the length of this vector to second order
+    const float px = fmaf(-w31, f2.x, fmaf(-w23, f1.x, vx));
+    const float py = fmaf(-w31, f2.y, fmaf(-w23, f1.y, vy));
+    const float pz = fmaf(-w31, f2.z, fmaf(-w23, f1.z, vz));
+    const float plane = fmaf(pz, pz, fmaf(py, py, px * px));
     const float s1 = __saturatef(a * f4.y), s2 = __saturatef(b * f4.z);
     const float e1 = fmaf(s1, fmaf(s1, f1.w, -2.f * a), vv);
-    const float e2 = fmaf(s2, fmaf(s2, f2.w, -2.f * b), vv);
+    const float e2b = fmaf(s2, fmaf(s2, f2.w, -2.f * b), vv);
     const float ux = vx - f1.x, uy = vy - f1.y, uz = vz - f1.z;       // x0 - x1
     const float c = fmaf(f3.z, uz, fmaf(f3.y, uy, f3.x * ux));
     const float uu = fmaf(uz, uz, fmaf(uy, uy, ux * ux));
     const float s3 = __saturatef(c * f4.w);
     const float e3 = fmaf(s3, fmaf(s3, f3.w, -2.f * c), uu);
-    const float edge = fminf(e1, fminf(e2, e3));
+    const float edge = fminf(e1, fminf(e2b, e3));
     const bool inside = (w23 >= 0.f) && (w31 >= 0.f) && (w12 >= 0.f);
+    e2 = 2e-6f * (vv + f1.w + f2.w + f3.w);
     return fmaxf(inside ? plane : edge, 0.f);
 }
 
@@ -333,10 +348,15 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
     const float INF = __int_as_float(0x7f800000);
     const V3 gx = node_pos(i, j, k, P);
     // stage-2 state (decides the result) and stage-1 state (decides who gets a stage-2 evaluation)
-    float best = valid ? (inside ? INF : R) : 0.f;
+    // like the reference's phi, the running minimum starts at `far` (makelevelset3.cpp:123): a triangle farther
+    // away than that never registers. Outside voxels may stop at the truncation radius instead.
+    const float start = inside ? far : fminf(R, far);
+    float best = valid ? start : 0.f;
     uint32_t best_t = 0xffffffffu;
-    float lim2 = valid ? (inside ? INF : fmaf(R + eta, R + eta, kappa)) : -1.f;   // pass iff cheap d^2 <= lim2
-    float besta2 = lim2;
+    // pass to stage 2 iff a2 - e2 <= lim2 = 1.002 * ub2 + kappa, ub2 = smallest a2 + e2 seen (start^2 at first)
+    float ub2 = valid ? start * start : -1.f;
+    float lim2 = valid ? fmaf(ub2, 1.002f, kappa) : -1.f;
+    (void)eta; (void)INF;
 
     const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
     const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
@@ -376,7 +396,7 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
             const uint32_t er = __shfl_sync(0xffffffffu, ent, r);
             const float dr = __shfl_sync(0xffffffffu, d, r);
             const uint32_t tr = er >> 5;
-            if ((int)(er & 31u) == lane && (dr < best || (dr == best && tr < best_t))) { best = dr; best_t = tr; }
+            if ((int)(er & 31u) == lane && (dr < best || (dr == best && best_t != 0xffffffffu && tr < best_t))) { best = dr; best_t = tr; }
         }
         __syncwarp();
     };
@@ -455,13 +475,13 @@ tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                     if (lane < 2) prefetch_l1(reinterpret_cast<const char*>(Fm + 5 * (int64_t)tn2) + lane * 64);
                 }
                 bool flagged;
-                const float a2 = fast_dist2(gx, Fm + 5 * (int64_t)t, flagged);
+                float e2;
+                const float a2 = fast_dist2(gx, Fm + 5 * (int64_t)t, flagged, e2);
                 n_pairs += valid ? 1 : 0;
-                const bool cand = valid && (flagged || !(a2 > lim2));
-                if (!flagged && a2 < besta2) {       // new cheap minimum: tighten the filter
-                    besta2 = a2;
-                    const float s = sqrtf(a2) * 1.001f + eta;
-                    lim2 = fmaf(s, s, kappa);
+                const bool cand = valid && (flagged || !(a2 - e2 > lim2));
+                if (!flagged && a2 + e2 < ub2) {     // new upper bound of the minimum: tighten the filter
+                    ub2 = a2 + e2;
+                    lim2 = fmaf(ub2, 1.002f, kappa);
                 }
                 const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                 if (cm) {

@@ -3,6 +3,7 @@ the compiled reference and the golden fixtures. Bit-exact for faithful mode."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -363,3 +364,11 @@ def test_host_abi_chunked_path_equals_device_abi(g3d):
         assert np.array_equal(_bits(sdf), _bits(r["sdf"].cpu().numpy()))
         assert np.array_equal(ct, r["closest_tri"].cpu().numpy())
     L.g3d_context_destroy(ctx)
+
+
+def test_randomised_parity_campaign(g3d):
+    """A short run of tools/fuzz_parity.py (random soups, degenerate / huge triangles, random grids and poses)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--meshes", "32", "--poses", "100",
+                          "--seed", "5"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
