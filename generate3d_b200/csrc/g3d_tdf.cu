@@ -45,7 +45,6 @@ struct TdfWs {
     float4*   tri;          // 4 x float4 per triangle: TriRec (g3d_ptd.cuh)
     int4*     box;          // i0|i1<<16, j0|j1<<16, k0|k1<<16, mesh
     u64*      key;
-    uint8_t*  chg;          // per node: 0 = closest_tri set by the band init, s+1 = last changed in sweep s
     uint32_t* parity;
     uint32_t* order;        // packed a | b<<10 | c<<20, grouped by level
     int32_t*  level_start;  // [nlev + 1]
@@ -71,7 +70,6 @@ TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params
     w.tri = (float4*)take((size_t)total_tris * 64);
     w.box = (int4*)take((size_t)total_tris * 16);
     w.key = (u64*)take((size_t)n_mesh * nvox * 8);
-    w.chg = (uint8_t*)take((size_t)n_mesh * nvox);
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
     w.order = (uint32_t*)take((size_t)nsweep * 4);
     w.level_start = (int32_t*)take((size_t)(nlev_of(p) + 2) * 4);
@@ -409,7 +407,7 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 //   1. a candidate equal to the node's own triangle, or to an earlier candidate of the same
 //      visit, cannot pass the strict `<`;
 //   2. a neighbour whose closest_tri has not changed since this node last examined it (in an
-//      earlier sweep that had the same neighbour upwind) cannot pass either. `chg` records the
+//      earlier sweep that had the same neighbour upwind) cannot pass either. The top 5 bits of a key's low word record the
 //      sweep in which each node last changed; s_prev[s][r] is the last earlier sweep in which
 //      slot r of sweep s pointed at the same absolute neighbour. The whole second pass of a
 //      converged field is skipped this way. Nodes on the grid boundary are not part of every
@@ -418,6 +416,7 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 //      pushes them into a private shared-memory queue, evaluates the queue densely (one pair
 //      per lane), and the owners then replay the results in neighbour order.
 constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
+constexpr uint32_t kTriMask = 0x7ffffffu;           // low 27 bits of a key's low word: closest_tri (all ones = none)
 
 __device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
 {
@@ -439,7 +438,7 @@ __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatil
 
 template <int NT, bool CL>
 __global__ void __launch_bounds__(NT)
-tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
+tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                  const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
                  int lev_words, g3d_tdf_params P, u64* counter)
 {
@@ -496,8 +495,9 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
     const int mesh = blockIdx.x / csize;
     const int64_t nvox = nvox_of(P);
     u64* K = key + (int64_t)mesh * nvox;
-    uint8_t* G = chg + (int64_t)mesh * nvox;
-    const int* Klo = (const int*)K;                // low word of each key = closest_tri
+    // low word of each key = change code << 27 | closest_tri (kTriNone when the node has no triangle yet): one
+    // 4-byte load tells both whether a neighbour needs to be examined and which triangle it holds
+    const uint32_t* Klo = (const uint32_t*)K;
     const float4* T = tri + 4 * tri_off[mesh];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int sj = ni, sk = ni * nj;
@@ -532,21 +532,16 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
                     const int cls = (i == 0 ? 0 : (i == ni - 1 ? 2 : 1)) + 3 * (j == 0 ? 0 : (j == nj - 1 ? 2 : 1)) +
                                     9 * (k == 0 ? 0 : (k == nk - 1 ? 2 : 1));
                     const int8_t* th = &s_thr[s][0][cls];
-                    const uint32_t look =
-                        ((int)G[n0] > th[0] ? 1u : 0u) | ((int)G[n1] > th[27] ? 2u : 0u) | ((int)G[n2] > th[54] ? 4u : 0u) |
-                        ((int)G[n3] > th[81] ? 8u : 0u) | ((int)G[n4] > th[108] ? 16u : 0u) | ((int)G[n5] > th[135] ? 32u : 0u) |
-                        ((int)G[n6] > th[162] ? 64u : 0u);
-                    if (look) {
-                        if (look & 1u) c0 = Klo[2 * n0];
-                        if (look & 2u) c1 = Klo[2 * n1];
-                        if (look & 4u) c2 = Klo[2 * n2];
-                        if (look & 8u) c3 = Klo[2 * n3];
-                        if (look & 16u) c4 = Klo[2 * n4];
-                        if (look & 32u) c5 = Klo[2 * n5];
-                        if (look & 64u) c6 = Klo[2 * n6];
+                    const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
+                                   w5 = Klo[2 * n5], w6 = Klo[2 * n6];
+#define G3D_CAND(w, off) (((int)((w) >> 27) > th[off] && ((w) & kTriMask) != kTriMask) ? (int)((w) & kTriMask) : -1)
+                    c0 = G3D_CAND(w0, 0); c1 = G3D_CAND(w1, 27); c2 = G3D_CAND(w2, 54); c3 = G3D_CAND(w3, 81);
+                    c4 = G3D_CAND(w4, 108); c5 = G3D_CAND(w5, 135); c6 = G3D_CAND(w6, 162);
+#undef G3D_CAND
+                    if ((c0 & c1 & c2 & c3 & c4 & c5 & c6) >= 0) {      // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
                         phi = __uint_as_float((uint32_t)(kv >> 32));
-                        ct = (int)(uint32_t)kv;
+                        ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);
                         need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
                         need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
                         need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
@@ -606,8 +601,7 @@ tdf_sweep_kernel(u64* key, uint8_t* chg, const float4* __restrict__ tri, const i
                     if (need & 64u) { d = q_res[r++]; if (d < phi) { phi = d; ct = c6; changed = true; } }
                     if (changed) {
                         const uint8_t code = (uint8_t)(s + 1);
-                        K[n] = ((u64)__float_as_uint(phi) << 32) | (uint32_t)ct;
-                        G[n] = code;
+                        K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)code << 27) | (uint32_t)ct;
                         if (!CL) {
                             // in every direction d this node is upwind of nodes 1..3 levels further on: stamp those
                             // levels (codes only grow and all writers of a sweep write the same value)
@@ -677,7 +671,7 @@ tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ pa
         if (valid) {
             u64 kv = K[idx];
             float phi = __uint_as_float((uint32_t)(kv >> 32));
-            ct = (int)(uint32_t)kv;
+            ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);   // top 5 bits: sweep bookkeeping
             if (inside) phi = -phi;
             sdf = mul(phi, P.out_scale);                                    // main.cpp:119
         }
@@ -750,7 +744,7 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL ? 1 : 0;
-    G3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, w.key, w.chg, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
+    G3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, w.key, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
                                     (const int32_t*)w.level_start, nlev, lev_words, p, cnt));
     return G3D_OK;
 }
@@ -813,8 +807,8 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
     if (rc != G3D_OK) return rc;
     if (p.mode != G3D_MODE_FAITHFUL && p.mode != G3D_MODE_EXACT) { set_error("tdf: unknown mode %d", p.mode); return G3D_ERR_INVALID; }
-    if (p.mode == G3D_MODE_EXACT && total_tris >= ((int64_t)1 << 27)) {   // stage-2 queue entries are t << 5 | lane
-        set_error("exact mode: at most 2^27 - 1 triangles per call, got %lld", (long long)total_tris);
+    if (total_tris >= ((int64_t)1 << 27) - 1) {      // closest_tri shares a 32-bit word with 5 bits of bookkeeping
+        set_error("at most 2^27 - 2 triangles per call, got %lld", (long long)total_tris);
         return G3D_ERR_INVALID;
     }
     if (n_mesh == 0) return G3D_OK;
@@ -837,7 +831,6 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     } else {
         TdfWs w = carve(ws, n_mesh, total_tris, p);
         key = w.key; parity = w.parity;
-        G3D_CUDA_TRY(cudaMemsetAsync(w.chg, 0, (size_t)n_mesh * nvox, stream));
     }
     tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
         key, n_mesh * nvox, init, parity, n_mesh * pw, out.status, n_mesh,
