@@ -163,7 +163,7 @@ int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_ver
     cudaStream_t s = (cudaStream_t)cuda_stream;
     int rc = tdf_begin(total_verts, total_tris, n_mesh, *params, *out, workspace, workspace_bytes, s);
     if (rc != G3D_OK) return rc;
-    rc = tdf_stage_tris(verts, vert_off, tris, tri_off, 0, total_tris, total_tris, n_mesh, *params, *out, workspace, s);
+    rc = tdf_stage_tris(verts, vert_off, tris, tri_off, 0, total_tris, 0, n_mesh, total_tris, n_mesh, *params, *out, workspace, s);
     if (rc != G3D_OK) return rc;
     rc = tdf_solve(tri_off, total_tris, n_mesh, *params, workspace, s);
     if (rc != G3D_OK) return rc;
@@ -346,7 +346,7 @@ int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_o
     for (int ch = 0; ch < nch; ++ch) {
         const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch);
         G3D_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_in[ch], 0));
-        rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], nt, n_mesh, *params, d, ws, s);
+        rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], m0, m1, nt, n_mesh, *params, d, ws, s);
         if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
     }
     rc = tdf_solve(dto, nt, n_mesh, *params, ws, s);

@@ -370,6 +370,221 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
     if (counter && n_eval) atomicAdd(counter, n_eval);
 }
 
+// Tiled variant for batches of small grids: one CTA owns a kTile^3 block of one mesh's grid and keeps its keys in
+// shared memory. Its warps scan the mesh's band boxes 32 at a time and collect the boxes that reach into the block;
+// the cull reads and the atomicMin go to shared memory: no L2 round trip in front of every test, a fresher phi (so
+// about half as many pairs survive), and the block is written out once with plain stores. A triangle whose band
+// spans several blocks is visited by each of them, for its own nodes only.
+//   Typical band boxes hold 27-64 nodes, so the per-triangle overhead of a warp-wide walk would dominate. Small
+// boxes (after clipping) are therefore walked one per LANE: 32 pending triangles at a time, each lane stepping
+// through the rows of its own box, one cull test per lane and step. Large boxes keep the
+// warp-wide walk. Survivors of both go to the same warp-private queue and are evaluated 32 at a time.
+constexpr int kTile = 16;
+constexpr int kLaneI = 8, kLaneRows = 64;            // lane-walked boxes: at most 8 wide in i, 64 (j, k) rows
+
+// One (node, triangle) pair per lane against the block's keys in shared memory. Kept out of line: the walk loops
+// below reach it from many unrolled sites and the evaluation is several hundred instructions long.
+__device__ __noinline__ void tile_eval_item(const float4* __restrict__ TR, u64* s_key, uint32_t t, uint32_t pos, int I0,
+                                            int J0, int K0, float dx, float ox, float oy, float oz, float far)
+{
+    const int i = pos & 1023u, j = (pos >> 10) & 1023u, k = pos >> 20;
+    const V3 gx = { add(mul((float)i, dx), ox), add(mul((float)j, dx), oy), add(mul((float)k, dx), oz) };   // node_pos
+    const float d = point_triangle_distance(gx, load_trirec(TR + 4 * (int64_t)t));
+    const int e = (i - I0) + kTile * ((j - J0) + kTile * (k - K0));
+    const float cur = __uint_as_float(((const volatile uint32_t*)s_key)[2 * e + 1]);
+    // d < far mirrors the very first `d < phi`; d <= cur lets an equal distance with a LOWER index through
+    if (d < far && d <= cur) atomicMin(s_key + e, ((u64)__float_as_uint(d) << 32) | t);
+}
+
+__global__ void __launch_bounds__(256)
+tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ box, const int64_t* __restrict__ tri_off,
+                      int mesh0, int nbx, int nby, int nbz, g3d_tdf_params P, u64* __restrict__ key, float far,
+                      u64* counter)
+{
+    __shared__ u64 s_key[kTile * kTile * kTile];
+    __shared__ uint32_t s_qt[8][64], s_qp[8][64], s_pend[8][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int per = nbx * nby * nbz;
+    const int mesh = mesh0 + (int)(blockIdx.x / (unsigned)per);
+    const int rb = (int)(blockIdx.x % (unsigned)per);
+    const int I0 = (rb % nbx) * kTile, J0 = ((rb / nbx) % nby) * kTile, K0 = (rb / (nbx * nby)) * kTile;
+    const int I1 = min(I0 + kTile, P.ni) - 1, J1 = min(J0 + kTile, P.nj) - 1, K1 = min(K0 + kTile, P.nk) - 1;
+    const u64 init = ((u64)__float_as_uint(far) << 32) | 0xffffffffull;
+    for (int e = threadIdx.x; e < kTile * kTile * kTile; e += 256) s_key[e] = init;
+    __syncthreads();
+    const volatile uint32_t* s_w = (const volatile uint32_t*)s_key;
+    uint32_t* qt = s_qt[wib];
+    uint32_t* qp = s_qp[wib];
+    uint32_t* pend = s_pend[wib];
+    int qn = 0, pn = 0;                             // queue / pending fill, warp-uniform
+    u64 n_eval = 0;
+    const int64_t tb = tri_off[mesh];
+    const int T = (int)(tri_off[mesh + 1] - tb);
+    const float4* TR = tri + 4 * tb;
+    const int4* BX = box + tb;
+
+    auto eval_item = [&](uint32_t t, uint32_t pos) {
+        tile_eval_item(TR, s_key, t, pos, I0, J0, K0, P.dx, P.origin[0], P.origin[1], P.origin[2], far);
+    };
+    // survivors of one step (warp-wide): compact into the queue, evaluate a full warp's worth when there is one
+    auto push = [&](bool pass, uint32_t t, uint32_t pos) {
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            if (pass) {
+                const int w = qn + __popc(m & lt);
+                qt[w] = t;
+                qp[w] = pos;
+            }
+            qn += __popc(m);
+            if (qn >= 32) {
+                __syncwarp();
+                qn -= 32;
+                eval_item(qt[qn + lane], qp[qn + lane]);
+                ++n_eval;
+                __syncwarp();
+            }
+        }
+    };
+    // squared distance from a node to the triangle's bounding box against the node's current phi
+    auto cull_pass = [&](int i, int j, int k, float lox, float hix, float loy, float hiy, float loz, float hiz) {
+        const V3 gx = node_pos(i, j, k, P);
+        const float cur = __uint_as_float(s_w[2 * ((i - I0) + kTile * ((j - J0) + kTile * (k - K0))) + 1]);
+        const float ex = fmaxf(0.f, fmaxf(lox - gx.x, gx.x - hix));
+        const float ey = fmaxf(0.f, fmaxf(loy - gx.y, gx.y - hiy));
+        const float ez = fmaxf(0.f, fmaxf(loz - gx.z, gx.z - hiz));
+        return !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(cur * cur, 1.001f, 1e-12f));
+    };
+    // one triangle per lane (t < 0: idle lane); boxes at most kLaneI nodes wide in i after clipping. The lane
+    // steps through the (j, k) rows of its box; along a row only the i term of the box distance changes, and
+    // those (at most kLaneI) squares are computed once per triangle.
+    auto walk_lanes = [&](int t) {
+        int i0 = I0, bi = 0, j0 = J0, j1 = J0 - 1, k0 = K0, nrow = 0;
+        float ex2[kLaneI];
+        float loy = 0.f, hiy = 0.f, loz = 0.f, hiz = 0.f;
+#pragma unroll
+        for (int a = 0; a < kLaneI; ++a) ex2[a] = 0.f;
+        if (t >= 0) {
+            const int4 b = __ldg(BX + t);
+            i0 = max(b.x & 0xffff, I0);
+            bi = min(b.x >> 16, I1) - i0 + 1;
+            j0 = max(b.y & 0xffff, J0); j1 = min(b.y >> 16, J1);
+            k0 = max(b.z & 0xffff, K0);
+            const int k1 = min(b.z >> 16, K1);
+            const float4 v1 = __ldg(TR + 4 * (int64_t)t), v2 = __ldg(TR + 4 * (int64_t)t + 1), v3 = __ldg(TR + 4 * (int64_t)t + 2);
+            const float lox = fminf(v1.x, fminf(v2.x, v3.x)), hix = fmaxf(v1.x, fmaxf(v2.x, v3.x));
+            loy = fminf(v1.y, fminf(v2.y, v3.y)); hiy = fmaxf(v1.y, fmaxf(v2.y, v3.y));
+            loz = fminf(v1.z, fminf(v2.z, v3.z)); hiz = fmaxf(v1.z, fmaxf(v2.z, v3.z));
+            nrow = (j1 - j0 + 1) * (k1 - k0 + 1);
+            // a non-finite vertex gives NaN distances, which never win: nothing to do for this triangle
+            if (!(fabsf(v1.x + v1.y + v1.z + v2.x + v2.y + v2.z + v3.x + v3.y + v3.z) < 3.0e38f)) nrow = 0;
+#pragma unroll
+            for (int a = 0; a < kLaneI; ++a) {
+                const float gx = add(mul((float)(i0 + a), P.dx), P.origin[0]);
+                const float ex = fmaxf(0.f, fmaxf(lox - gx, gx - hix));
+                ex2[a] = ex * ex;
+            }
+        }
+        const int rmax = __reduce_max_sync(0xffffffffu, nrow), bimax = __reduce_max_sync(0xffffffffu, bi);
+        int j = j0, k = k0;
+        for (int r = 0; r < rmax; ++r) {
+            const bool rv = r < nrow;
+            const float gy = add(mul((float)j, P.dx), P.origin[1]), gz = add(mul((float)k, P.dx), P.origin[2]);
+            const float ey = fmaxf(0.f, fmaxf(loy - gy, gy - hiy)), ez = fmaxf(0.f, fmaxf(loz - gz, gz - hiz));
+            const float eyz2 = fmaf(ey, ey, ez * ez);
+            const int e = (i0 - I0) + kTile * ((j - J0) + kTile * (k - K0));
+            const uint32_t pos = (uint32_t)i0 | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+#pragma unroll
+            for (int a = 0; a < kLaneI; ++a) {
+                if (a >= bimax) break;
+                bool pass = false;
+                if (rv && a < bi) {
+                    const float cur = __uint_as_float(s_w[2 * (e + a) + 1]);
+                    pass = !(ex2[a] + eyz2 > fmaf(cur * cur, 1.001f, 1e-12f));
+                }
+                push(pass, (uint32_t)t, pos + (uint32_t)a);
+            }
+            if (++j > j1) { j = j0; ++k; }
+        }
+    };
+    // the whole warp on one (large) box
+    auto walk_warp = [&](int t, int bxw, int byw, int bzw) {
+        const int i0 = max(bxw & 0xffff, I0), i1 = min(bxw >> 16, I1), j0 = max(byw & 0xffff, J0),
+                  j1 = min(byw >> 16, J1), k0 = max(bzw & 0xffff, K0), k1 = min(bzw >> 16, K1);
+        const int bi = i1 - i0 + 1, bj = j1 - j0 + 1, bk = k1 - k0 + 1;
+        const float4 v1 = __ldg(TR + 4 * (int64_t)t), v2 = __ldg(TR + 4 * (int64_t)t + 1), v3 = __ldg(TR + 4 * (int64_t)t + 2);
+        const float lox = fminf(v1.x, fminf(v2.x, v3.x)), hix = fmaxf(v1.x, fmaxf(v2.x, v3.x));
+        const float loy = fminf(v1.y, fminf(v2.y, v3.y)), hiy = fmaxf(v1.y, fmaxf(v2.y, v3.y));
+        const float loz = fminf(v1.z, fminf(v2.z, v3.z)), hiz = fmaxf(v1.z, fmaxf(v2.z, v3.z));
+        if (!(fabsf(v1.x + v1.y + v1.z + v2.x + v2.y + v2.z + v3.x + v3.y + v3.z) < 3.0e38f)) return;
+        const int n = bi * bj * bk;                      // <= kTile^3
+        const float rbi = 1.0f / (float)bi, rbj = 1.0f / (float)bj;
+        for (int q0 = 0; q0 < n; q0 += 32) {
+            const int q = q0 + lane;
+            bool pass = false;
+            uint32_t pos = 0;
+            if (q < n) {
+                const int r = (int)(((float)q + 0.5f) * rbi);     // exact for q < 2^20, see above
+                int k = (int)(((float)r + 0.5f) * rbj);
+                const int i = i0 + (q - r * bi);
+                const int j = j0 + (r - k * bj);
+                k += k0;
+                pass = cull_pass(i, j, k, lox, hix, loy, hiy, loz, hiz);
+                pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+            }
+            push(pass, (uint32_t)t, pos);
+        }
+    };
+
+    for (int base = wib * 32; base < T; base += 8 * 32) {
+        const int tl = base + lane;
+        int4 b = make_int4(1, 1, 1, 0);
+        bool small = false, large = false;
+        if (tl < T) {
+            b = __ldg(BX + tl);
+            const int ci = min(b.x >> 16, I1) - max(b.x & 0xffff, I0) + 1, cj = min(b.y >> 16, J1) - max(b.y & 0xffff, J0) + 1,
+                      ck = min(b.z >> 16, K1) - max(b.z & 0xffff, K0) + 1;
+            if (ci > 0 && cj > 0 && ck > 0) {
+                prefetch_l1(TR + 4 * (int64_t)tl);
+                large = ci > kLaneI || cj * ck > kLaneRows;
+                small = !large;
+            }
+        }
+        uint32_t hm = __ballot_sync(0xffffffffu, large);
+        while (hm) {
+            const int src = __ffs(hm) - 1;
+            hm &= hm - 1;
+            walk_warp(base + src, __shfl_sync(0xffffffffu, b.x, src), __shfl_sync(0xffffffffu, b.y, src),
+                      __shfl_sync(0xffffffffu, b.z, src));
+        }
+        const uint32_t sm = __ballot_sync(0xffffffffu, small);
+        if (sm) {
+            if (small) pend[pn + __popc(sm & lt)] = (uint32_t)tl;
+            pn += __popc(sm);
+            if (pn >= 32) {
+                __syncwarp();
+                pn -= 32;
+                walk_lanes((int)pend[pn + lane]);
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    if (pn > 0) walk_lanes(lane < pn ? (int)pend[lane] : -1);
+    __syncwarp();
+    if (lane < qn) {
+        eval_item(qt[lane], qp[lane]);
+        ++n_eval;
+    }
+    __syncthreads();
+    u64* K = key + (int64_t)mesh * nvox_of(P);
+    for (int e = threadIdx.x; e < kTile * kTile * kTile; e += 256) {
+        const int i = I0 + (e % kTile), j = J0 + (e / kTile) % kTile, k = K0 + e / (kTile * kTile);
+        if (i <= I1 && j <= J1 && k <= K1) K[i + (int64_t)P.ni * (j + (int64_t)P.nj * k)] = s_key[e];
+    }
+    if (counter && n_eval) atomicAdd(counter, n_eval);
+}
+
 // ----------------------------------------------------------- sweep order ----
 // Nodes of the sweep lattice (ni-1)(nj-1)(nk-1) grouped by level a+b+c.
 __global__ void __launch_bounds__(1024)
@@ -841,7 +1056,7 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
 }
 
 int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* tris, const int64_t* tri_off,
-                   int64_t t0, int64_t t1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
+                   int64_t t0, int64_t t1, int32_t m0, int32_t m1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
                    const g3d_tdf_outputs& out, void* ws, cudaStream_t stream)
 {
     if (n_mesh == 0 || t1 <= t0) return G3D_OK;
@@ -857,8 +1072,18 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* 
         tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
             verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr);
         prof_mark(ST_PREP, stream);
-        tdf_init_kernel<<<grid_for((t1 - t0) * 32, 256, sms * 32), 256, 0, stream>>>(
-            w.tri, w.box, tri_off, t0, t1, p, w.key, far, prof_counters());
+        // [t0, t1) are the triangles of meshes [m0, m1). Batches of small grids: one CTA per 16^3 block of a mesh, keys in
+        // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel.
+        const int nbx = (p.ni + kTile - 1) / kTile, nby = (p.nj + kTile - 1) / kTile, nbz = (p.nk + kTile - 1) / kTile;
+        static int tiled = -1;                      // G3D_INIT_TILED=0/1 overrides the choice
+        if (tiled < 0) { const char* e = getenv("G3D_INIT_TILED"); tiled = e ? (atoi(e) ? 1 : 0) : 2; }
+        const bool use_tiled = tiled == 2 ? ((int64_t)nbx * nby * nbz <= 64) : tiled == 1;
+        if (use_tiled && (int64_t)(m1 - m0) * nbx * nby * nbz < (int64_t)INT_MAX)
+            tdf_init_tiled_kernel<<<(unsigned)((int64_t)(m1 - m0) * nbx * nby * nbz), 256, 0, stream>>>(
+                w.tri, w.box, tri_off, m0, nbx, nby, nbz, p, w.key, far, prof_counters());
+        else
+            tdf_init_kernel<<<grid_for((t1 - t0) * 32, 256, sms * 32), 256, 0, stream>>>(
+                w.tri, w.box, tri_off, t0, t1, p, w.key, far, prof_counters());
         prof_mark(ST_INIT, stream);
     }
     G3D_CUDA_TRY(cudaGetLastError());
