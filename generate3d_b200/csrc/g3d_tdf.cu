@@ -396,7 +396,7 @@ __device__ __noinline__ void tile_eval_item(const float4* __restrict__ TR, u64* 
     if (d < far && d <= cur) atomicMin(s_key + e, ((u64)__float_as_uint(d) << 32) | t);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ box, const int64_t* __restrict__ tri_off,
                       int mesh0, int nbx, int nby, int nbz, g3d_tdf_params P, u64* __restrict__ key, float far,
                       u64* counter)
