@@ -1075,11 +1075,12 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* 
             verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr);
         prof_mark(ST_PREP, stream);
         // [t0, t1) are the triangles of meshes [m0, m1). Batches of small grids: one CTA per 16^3 block of a mesh, keys in
-        // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel.
+        // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel, and so do
+        // batches too small to give every SM a block.
         const int nbx = (p.ni + kTile - 1) / kTile, nby = (p.nj + kTile - 1) / kTile, nbz = (p.nk + kTile - 1) / kTile;
         static int tiled = -1;                      // G3D_INIT_TILED=0/1 overrides the choice
         if (tiled < 0) { const char* e = getenv("G3D_INIT_TILED"); tiled = e ? (atoi(e) ? 1 : 0) : 2; }
-        const bool use_tiled = tiled == 2 ? ((int64_t)nbx * nby * nbz <= 64) : tiled == 1;
+        const bool use_tiled = tiled == 2 ? ((int64_t)nbx * nby * nbz <= 64 && (int64_t)(m1 - m0) * nbx * nby * nbz >= 2 * sms) : tiled == 1;
         if (use_tiled && (int64_t)(m1 - m0) * nbx * nby * nbz < (int64_t)INT_MAX)
             tdf_init_tiled_kernel<<<(unsigned)((int64_t)(m1 - m0) * nbx * nby * nbz), 256, 0, stream>>>(
                 w.tri, w.box, tri_off, m0, nbx, nby, nbz, p, w.key, far, prof_counters());
