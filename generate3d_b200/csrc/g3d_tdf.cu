@@ -1078,8 +1078,8 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* 
         // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel, and so do
         // batches too small to give every SM a block.
         const int nbx = (p.ni + kTile - 1) / kTile, nby = (p.nj + kTile - 1) / kTile, nbz = (p.nk + kTile - 1) / kTile;
-        static int tiled = -1;                      // G3D_INIT_TILED=0/1 overrides the choice
-        if (tiled < 0) { const char* e = getenv("G3D_INIT_TILED"); tiled = e ? (atoi(e) ? 1 : 0) : 2; }
+        const char* env_tiled = getenv("G3D_INIT_TILED");   // 0/1 overrides the choice (read per call: tests flip it)
+        const int tiled = env_tiled ? (atoi(env_tiled) ? 1 : 0) : 2;
         const bool use_tiled = tiled == 2 ? ((int64_t)nbx * nby * nbz <= 64 && (int64_t)(m1 - m0) * nbx * nby * nbz >= 2 * sms) : tiled == 1;
         if (use_tiled && (int64_t)(m1 - m0) * nbx * nby * nbz < (int64_t)INT_MAX)
             tdf_init_tiled_kernel<<<(unsigned)((int64_t)(m1 - m0) * nbx * nby * nbz), 256, 0, stream>>>(

@@ -366,9 +366,63 @@ def test_host_abi_chunked_path_equals_device_abi(g3d):
     L.g3d_context_destroy(ctx)
 
 
-def test_randomised_parity_campaign(g3d):
-    """A short run of tools/fuzz_parity.py (random soups, degenerate / huge triangles, random grids and poses)."""
+@pytest.mark.parametrize("tiled", [None, "1"])
+def test_randomised_parity_campaign(g3d, tiled):
+    """A short run of tools/fuzz_parity.py (random soups, degenerate / huge triangles, random grids and poses), once
+    with the kernel choice left to the library (single meshes: scatter band init) and once with the tiled band init
+    forced for every case."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--meshes", "32", "--poses", "100",
-                          "--seed", "5"], capture_output=True, text=True, timeout=900)
+    env = dict(os.environ)
+    env.pop("G3D_INIT_TILED", None)
+    if tiled:
+        env["G3D_INIT_TILED"] = tiled
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--meshes", "32",
+                          "--poses", "100" if tiled is None else "0", "--seed", "5"],
+                         capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("tiled", ["0", "1", None])
+def test_band_init_kernels_match_oracle_on_ragged_multiblock_batch(g3d, oracle, tiled, monkeypatch):
+    """Both band-init kernels (scatter with global atomics / tiled with the keys of a 16^3 block in shared memory) on
+    a batch whose grid is not a multiple of the tile and whose triangles range from sub-voxel to larger than the
+    grid; phi and closest_tri bit for bit against the oracle for every mesh. `None` leaves the choice to the library
+    (48 meshes x 12 blocks: tiled on a B200)."""
+    from generate3d_b200 import dfgen, _lib
+    if tiled is None:
+        monkeypatch.delenv("G3D_INIT_TILED", raising=False)
+    else:
+        monkeypatch.setenv("G3D_INIT_TILED", tiled)
+    rng = np.random.default_rng(2024)
+    ni, nj, nk = 20, 37, 45
+    Vs, Ts, vo, to = [], [], [0], [0]
+    for m in range(48):
+        kind = m % 4
+        if kind == 0:
+            v, t = S.table_mesh(int(rng.integers(2, 9)), 500 + m, scale=rng.uniform(0.4, 1.0), rot_y=rng.uniform(0, 6.28))
+        elif kind == 1:
+            v = rng.uniform(-0.6, 0.6, (60, 3)).astype(np.float32)
+            t = rng.integers(0, 60, (int(rng.integers(1, 200)), 3)).astype(np.uint32)
+        elif kind == 2:                                            # a few triangles larger than the grid
+            v = rng.uniform(-3, 3, (12, 3)).astype(np.float32)
+            t = rng.integers(0, 12, (int(rng.integers(1, 6)), 3)).astype(np.uint32)
+        else:                                                      # long thin triangles: wide in i, few (j, k) rows
+            v = rng.uniform(-0.5, 0.5, (40, 3)).astype(np.float32)
+            v[:, 1:] *= np.float32(0.05)
+            t = rng.integers(0, 40, (int(rng.integers(1, 80)), 3)).astype(np.uint32)
+        Vs.append(v); Ts.append(t)
+        vo.append(vo[-1] + len(v)); to.append(to[-1] + len(t))
+    V, T = np.concatenate(Vs), np.concatenate(Ts)
+    p = _lib.TdfParams()
+    p.ni, p.nj, p.nk = ni, nj, nk
+    origin = np.array([-0.5, -0.55, -0.6], np.float32)
+    dx = np.float32(1.0 / 36)
+    p.origin[:] = [float(x) for x in origin]
+    p.dx, p.out_scale, p.trunc, p.occ_thresh, p.mode, p.exact_band = float(dx), 1.0, float("inf"), 1.0, 0, 1
+    r = dfgen.tdf_batch_params(V, np.array(vo), T, np.array(to), p, ("sdf", "closest_tri", "status"))
+    assert not r["status"].cpu().numpy().any()
+    sdf, ct = r["sdf"].cpu().numpy(), r["closest_tri"].cpu().numpy()
+    for m in range(48):
+        want = oracle.make_level_set3(Ts[m], Vs[m], origin, dx, ni, nj, nk)
+        assert np.array_equal(_bits(sdf[m]), _bits(want["phi"])), m
+        assert np.array_equal(ct[m], want["closest_tri"]), m
