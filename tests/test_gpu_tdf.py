@@ -339,25 +339,27 @@ def test_faithful_single_huge_triangle_and_outside_mesh(g3d, oracle):
         assert np.array_equal(ct.cpu().numpy(), want["closest_tri"])
 
 
-def test_host_abi_chunked_path_equals_device_abi(g3d):
-    """>= 64 meshes: the host front end stages triangles in 4 chunks on a copy stream; results must equal the
-    one-shot device API bit for bit (faithful and exact)."""
+@pytest.mark.parametrize("count,n", [(70, 3), (640, 1)])
+def test_host_abi_chunked_path_equals_device_abi(g3d, count, n):
+    """>= 64 meshes: the host front end stages triangles in 4 chunks on a copy stream and returns results per chunk.
+    Results must equal the one-shot device API bit for bit (faithful and exact), also when the same context is
+    used again (arena and event reuse); 640 meshes is enough for the tiled band init to be chosen per chunk."""
     from generate3d_b200 import dfgen
-    V, voff, T, toff = S.table_batch(70, 3, first_seed=300)
+    V, voff, T, toff = S.table_batch(count, n, first_seed=300)
     L = g3d.lib()
     ctx = C.c_void_p()
     g3d.check(L.g3d_context_create(0, C.byref(ctx)))
-    for mode in (0, 1):
+    for mode in (0, 1, 0):
         p = g3d.TdfParams()
         g2w = np.zeros(16, np.float32)
         g3d.check(L.g3d_dfgen_geometry(32, 0, 1, None, None, C.byref(p), g2w.ctypes.data))
         p.trunc, p.occ_thresh, p.mode = 3.0, 1.0, mode
-        sdf = np.empty((70, 32, 32, 32), np.float32)
-        ct = np.empty((70, 32, 32, 32), np.int32)
-        status = np.empty(70, np.int32)
+        sdf = np.empty((count, 32, 32, 32), np.float32)
+        ct = np.empty((count, 32, 32, 32), np.int32)
+        status = np.empty(count, np.int32)
         o = g3d.TdfOutputs()
         o.sdf, o.closest_tri, o.status = sdf.ctypes.data, ct.ctypes.data, status.ctypes.data
-        g3d.check(L.g3d_tdf_batch_host(ctx, V.ctypes.data, voff.ctypes.data, T.ctypes.data, toff.ctypes.data, 70,
+        g3d.check(L.g3d_tdf_batch_host(ctx, V.ctypes.data, voff.ctypes.data, T.ctypes.data, toff.ctypes.data, count,
                                        C.byref(p), C.byref(o)))
         r = dfgen.tdf_batch(V, voff, T, toff, mode="faithful" if mode == 0 else "exact", outputs=("sdf", "closest_tri", "status"))
         assert not status.any()
