@@ -590,25 +590,38 @@ tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ b
 __global__ void __launch_bounds__(1024)
 tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order, int32_t* __restrict__ level_start)
 {
-    extern __shared__ int32_t s_cnt[];             // [nlev + 1]
-    for (int l = threadIdx.x; l <= nlev; l += blockDim.x) s_cnt[l] = 0;
-    __syncthreads();
-    int64_t n = (int64_t)na * nb * nc;
-    for (int64_t q = threadIdx.x; q < n; q += blockDim.x) {
-        int a = (int)(q % na), r = (int)(q / na);
-        atomicAdd(&s_cnt[a + r % nb + r / nb], 1);
-    }
-    __syncthreads();
+    // Closed form, no atomics: within a level nodes are sorted by (c, b). Neighbouring lanes of a sweep warp then
+    // hold neighbouring grid rows, whose upwind rows coincide, so a warp's loads fall into few cache lines -- and
+    // the order is the same on every run.
+    //   cnt2(m) = #{(a, b): a + b = m};  F(x) = sum of cnt2 up to x;  nodes of level l in slabs c' < c: F(l) - F(l - c).
+    extern __shared__ int32_t s_tab[];             // F[na + nb - 1], then level starts [nlev + 1]
+    const int nm = na + nb - 1;
+    int32_t* F = s_tab;
+    int32_t* ls = s_tab + nm;
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int l = 0; l < nlev; ++l) { int c = s_cnt[l]; s_cnt[l] = acc; level_start[l] = acc; acc += c; }
+        for (int m = 0; m < nm; ++m) {
+            acc += min(min(m, na + nb - 2 - m), min(na, nb) - 1) + 1;
+            F[m] = acc;
+        }
+        auto Fx = [&](int x) { return x < 0 ? 0 : F[min(x, nm - 1)]; };
+        acc = 0;
+        for (int l = 0; l < nlev; ++l) {
+            ls[l] = acc;
+            level_start[l] = acc;
+            acc += Fx(l) - Fx(l - nc);
+        }
+        ls[nlev] = acc;
         level_start[nlev] = acc;
     }
     __syncthreads();
+    auto Fx = [&](int x) { return x < 0 ? 0 : F[min(x, nm - 1)]; };
+    const int64_t n = (int64_t)na * nb * nc;
     for (int64_t q = threadIdx.x; q < n; q += blockDim.x) {
-        int a = (int)(q % na), r = (int)(q / na);
-        int b = r % nb, c = r / nb;
-        int pos = atomicAdd(&s_cnt[a + b + c], 1);
+        const int a = (int)(q % na), r = (int)(q / na);
+        const int b = r % nb, c = r / nb;
+        const int m = a + b, l = m + c;
+        const int pos = ls[l] + Fx(l) - Fx(l - c) + (b - max(0, m - (na - 1)));
         order[pos] = (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)c << 20);
     }
 }
@@ -1136,7 +1149,7 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
         TdfWs w = carve(ws, n_mesh, total_tris, p);
         const int nlev = nlev_of(p);
         if (total_tris > 0 && nlev > 0) {
-            size_t smem = (size_t)(nlev + 1) * 4;
+            size_t smem = (size_t)(nlev + 1 + (p.ni - 1) + (p.nj - 1) - 1) * 4;
             tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start);
             prof_mark(ST_ORDER, stream);
             int rc = launch_sweep(n_mesh, nlev, w, tri_off, p, cnt, stream);
