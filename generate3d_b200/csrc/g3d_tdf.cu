@@ -52,6 +52,22 @@ struct TdfWs {
 };
 
 __host__ __device__ inline int64_t nvox_of(const g3d_tdf_params& p) { return (int64_t)p.ni * p.nj * p.nk; }
+
+// Faithful-mode keys are stored in 4x4x4 bricks (512 B), x fastest inside a brick, so that one 128-byte line is a
+// 4x4 (i, j) patch of one k-slice. A sweep touches a node together with its 7 upwind neighbours (a 2x2x2 cube) and
+// visits the grid by anti-diagonal levels: in the linear layout a line (16 nodes along i) stays live for 18 levels
+// and the lines in use per mesh (~70 KB) times the meshes resident on an SM overflow the L1; a patch line is live
+// for 9 levels, the lanes of a warp share lines, and the live set (~25 KB per mesh) fits.
+// index = kx(i) + ky(j) + kz(k), separable so that the 8 indices of a cube cost six terms and eight sums.
+struct KeyMap { int sbj, sbk; int64_t stride; };    // key steps of one brick in j and in k; keys per mesh
+__host__ __device__ inline KeyMap keymap_of(const g3d_tdf_params& p)
+{
+    const int nbi = (p.ni + 3) >> 2, nbj = (p.nj + 3) >> 2, nbk = (p.nk + 3) >> 2;
+    return { 64 * nbi, 64 * nbi * nbj, (int64_t)64 * nbi * nbj * nbk };
+}
+__device__ __forceinline__ int kx(int i) { return ((i >> 2) << 6) | (i & 3); }
+__device__ __forceinline__ int ky(int j, int sbj) { return (j >> 2) * sbj + ((j & 3) << 2); }
+__device__ __forceinline__ int kz(int k, int sbk) { return (k >> 2) * sbk + ((k & 3) << 4); }
 inline int nlev_of(const g3d_tdf_params& p)
 {
     int l = (p.ni - 2) + (p.nj - 2) + (p.nk - 2) + 1;
@@ -69,7 +85,7 @@ TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params
     if (nsweep < 0) nsweep = 0;
     w.tri = (float4*)take((size_t)total_tris * 64);
     w.box = (int4*)take((size_t)total_tris * 16);
-    w.key = (u64*)take((size_t)n_mesh * nvox * 8);
+    w.key = (u64*)take((size_t)n_mesh * keymap_of(p).stride * 8);       // bricked, padded to whole bricks
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
     w.order = (uint32_t*)take((size_t)nsweep * 4);
     w.level_start = (int32_t*)take((size_t)(nlev_of(p) + 2) * 4);
@@ -278,7 +294,8 @@ __device__ __forceinline__ void init_eval_item(uint32_t t, uint32_t pos, const f
     const int i = pos & 1023u, j = (pos >> 10) & 1023u, k = pos >> 20;
     const int mesh = __ldg(box + t).w;
     const float d = point_triangle_distance(node_pos(i, j, k, P), load_trirec(tri + 4 * (int64_t)t));
-    u64* kp = key + (int64_t)mesh * nvox + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k));
+    const KeyMap km = keymap_of(P);
+    u64* kp = key + (int64_t)mesh * km.stride + (kx(i) + ky(j, km.sbj) + kz(k, km.sbk));
     const float cur = __uint_as_float((uint32_t)(__ldca(kp) >> 32));
     // d < far mirrors the very first `d < phi`; d <= cur lets an equal distance with a LOWER
     // triangle index through, as the serial loop would
@@ -299,6 +316,7 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t nvox = nvox_of(P);
+    const KeyMap km = keymap_of(P);
     for (int64_t t = t_first + warp; t < total_tris; t += nwarp) {
         if (lane < 2 && t + nwarp < total_tris) {    // the next triangle's box and record are two dependent loads away
             if (lane == 0) prefetch_l1(box + t + nwarp);
@@ -314,7 +332,7 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
         const float loz = fminf(v1.z, fminf(v2.z, v3.z)), hiz = fmaxf(v1.z, fmaxf(v2.z, v3.z));
         // a non-finite vertex gives NaN distances, which never win: nothing to do for this triangle
         if (!(fabsf(v1.x + v1.y + v1.z + v2.x + v2.y + v2.z + v3.x + v3.y + v3.z) < 3.0e38f)) continue;
-        const u64* K = key + (int64_t)b.w * nvox;
+        const u64* K = key + (int64_t)b.w * km.stride;
         const int n = bi * bj * bk;
         const float rbi = 1.0f / (float)bi, rbj = 1.0f / (float)bj;
         for (int q0 = 0; q0 < n; q0 += 32) {
@@ -337,7 +355,7 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
                 const int j = j0 + (r - k * bj);
                 k += k0;
                 const V3 gx = node_pos(i, j, k, P);
-                const float cur = __uint_as_float((uint32_t)(__ldca(K + (i + (int64_t)P.ni * (j + (int64_t)P.nj * k))) >> 32));
+                const float cur = __uint_as_float((uint32_t)(__ldca(K + (kx(i) + ky(j, km.sbj) + kz(k, km.sbk))) >> 32));
                 const float ex = fmaxf(0.f, fmaxf(lox - gx.x, gx.x - hix));
                 const float ey = fmaxf(0.f, fmaxf(loy - gx.y, gx.y - hiy));
                 const float ez = fmaxf(0.f, fmaxf(loz - gx.z, gx.z - hiz));
@@ -577,10 +595,11 @@ tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ b
         ++n_eval;
     }
     __syncthreads();
-    u64* K = key + (int64_t)mesh * nvox_of(P);
+    const KeyMap km = keymap_of(P);
+    u64* K = key + (int64_t)mesh * km.stride;
     for (int e = threadIdx.x; e < kTile * kTile * kTile; e += 256) {
         const int i = I0 + (e % kTile), j = J0 + (e / kTile) % kTile, k = K0 + e / (kTile * kTile);
-        if (i <= I1 && j <= J1 && k <= K1) K[i + (int64_t)P.ni * (j + (int64_t)P.nj * k)] = s_key[e];
+        if (i <= I1 && j <= J1 && k <= K1) K[kx(i) + ky(j, km.sbj) + kz(k, km.sbk)] = s_key[e];
     }
     if (counter && n_eval) atomicAdd(counter, n_eval);
 }
@@ -723,19 +742,17 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     __syncthreads();
     const int csize = CL ? (int)cluster_nctarank() : 1, crank = CL ? (int)cluster_ctarank() : 0;
     const int mesh = blockIdx.x / csize;
-    const int64_t nvox = nvox_of(P);
-    u64* K = key + (int64_t)mesh * nvox;
+    const KeyMap km = keymap_of(P);
+    u64* K = key + (int64_t)mesh * km.stride;
     // low word of each key = change code << 27 | closest_tri (kTriNone when the node has no triangle yet): one
     // 4-byte load tells both whether a neighbour needs to be examined and which triangle it holds
     const uint32_t* Klo = (const uint32_t*)K;
     const float4* T = tri + 4 * tri_off[mesh];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
-    const int sj = ni, sk = ni * nj;
 
     for (int s = 0; s < 16; ++s) {
         int di, dj, dk;
         sweep_dir(s, di, dj, dk);
-        const int oi = di, oj = dj * sj, ok = dk * sk;
         const int tmin = s_tmin[s];
         const uint8_t* dirty = s_dirty + (s & 7) * nlev;
         for (int L = 0; L < nlev; ++L) {
@@ -755,10 +772,12 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     int j = dj > 0 ? 1 + b : nj - 2 - b;
                     int k = dk > 0 ? 1 + c : nk - 2 - c;
                     pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
-                    n = i + sj * j + sk * k;
-                    // the 7 upwind neighbours in the order of cpp:72-78
-                    const int n0 = n - oi, n1 = n - oj, n2 = n - oi - oj, n3 = n - ok, n4 = n - oi - ok,
-                              n5 = n - oj - ok, n6 = n - oi - oj - ok;
+                    // the node and its 7 upwind neighbours (in the order of cpp:72-78) in the bricked key layout
+                    const int x0 = kx(i), x1 = kx(i - di), y0 = ky(j, km.sbj), y1 = ky(j - dj, km.sbj),
+                              z0 = kz(k, km.sbk), z1 = kz(k - dk, km.sbk);
+                    n = x0 + y0 + z0;
+                    const int n0 = x1 + y0 + z0, n1 = x0 + y1 + z0, n2 = x1 + y1 + z0, n3 = x0 + y0 + z1,
+                              n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
                     const int cls = (i == 0 ? 0 : (i == ni - 1 ? 2 : 1)) + 3 * (j == 0 ? 0 : (j == nj - 1 ? 2 : 1)) +
                                     9 * (k == 0 ? 0 : (k == nk - 1 ? 2 : 1));
                     const int8_t* th = &s_thr[s][0][cls];
@@ -870,7 +889,7 @@ __device__ __forceinline__ float log_transform(float x)
 __global__ void __launch_bounds__(256)
 tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ parity,
                     const int64_t* __restrict__ vert_off, const int64_t* __restrict__ tri_off, int mesh0, int n_mesh,
-                    g3d_tdf_params P, g3d_tdf_outputs O, int signed_mode)
+                    g3d_tdf_params P, g3d_tdf_outputs O, int signed_mode, int bricked)
 {
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (mesh - mesh0, k, j)
@@ -880,7 +899,10 @@ tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ pa
     int mesh = (int)(row / ((int64_t)P.nk * P.nj));
     int64_t nvox = nvox_of(P), pw = (nvox + 31) / 32;
     int64_t rbase = (row - (int64_t)mesh * P.nk * P.nj) * P.ni;           // node index of i = 0
-    const u64* K = key + (int64_t)mesh * nvox;
+    const KeyMap km = keymap_of(P);
+    const u64* K = key + (int64_t)mesh * (bricked ? km.stride : nvox);
+    const int rj = (int)((row - (int64_t)mesh * P.nk * P.nj) % P.nj), rk = (int)((row - (int64_t)mesh * P.nk * P.nj) / P.nj);
+    const int kyz = ky(rj, km.sbj) + kz(rk, km.sbk);
     const uint32_t* par = parity + (int64_t)mesh * pw;
     const bool aligned = (P.ni & 31) == 0;
     if (O.status && lane == 0 && rbase == 0 &&
@@ -899,7 +921,7 @@ tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ pa
         float sdf = 0.f;
         int ct = -1;
         if (valid) {
-            u64 kv = K[idx];
+            u64 kv = K[bricked ? (int64_t)(kx(i) + kyz) : idx];
             float phi = __uint_as_float((uint32_t)(kv >> 32));
             ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);   // top 5 bits: sweep bookkeeping
             if (inside) phi = -phi;
@@ -1062,8 +1084,9 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
         TdfWs w = carve(ws, n_mesh, total_tris, p);
         key = w.key; parity = w.parity;
     }
-    tdf_fill_kernel<<<grid_for(n_mesh * nvox, 256, sms * 16), 256, 0, stream>>>(
-        key, n_mesh * nvox, init, parity, n_mesh * pw, out.status, n_mesh,
+    const int64_t n_key = (int64_t)n_mesh * (p.mode == G3D_MODE_EXACT ? nvox : keymap_of(p).stride);
+    tdf_fill_kernel<<<grid_for(n_key, 256, sms * 16), 256, 0, stream>>>(
+        key, n_key, init, parity, n_mesh * pw, out.status, n_mesh,
         (out.occ_bits && (p.ni & 31)) ? out.occ_bits : nullptr, n_mesh * pw);
     prof_mark(ST_FILL, stream);
     G3D_CUDA_TRY(cudaGetLastError());
@@ -1170,7 +1193,7 @@ int tdf_finalize(const int64_t* vert_off, const int64_t* tri_off, int64_t total_
     if (p.mode == G3D_MODE_EXACT) { exact::Ws w = exact::carve(ws, n_mesh, total_tris, p); key = w.key; parity = w.parity; }
     else { TdfWs w = carve(ws, n_mesh, total_tris, p); key = w.key; parity = w.parity; }
     tdf_finalize_kernel<<<(unsigned)(((int64_t)(m1 - m0) * p.nk * p.nj * 32 + 255) / 256), 256, 0, stream>>>(
-        key, parity, vert_off, tri_off, m0, m1 - m0, p, out, 1);
+        key, parity, vert_off, tri_off, m0, m1 - m0, p, out, 1, p.mode == G3D_MODE_EXACT ? 0 : 1);
     prof_mark(ST_FINAL, stream);
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
