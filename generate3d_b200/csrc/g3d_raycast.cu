@@ -48,19 +48,24 @@ __device__ __forceinline__ int round_clamp(float p, int cmax)
 }
 
 // u = (x*f)/|z| + c rounded half-to-even and clamped, as the reference computes it (raytracing.py:71-75), but the
-// IEEE division is only paid when it can matter: a reciprocal-multiply estimate is within a few ulp of the
-// exactly rounded u (rcp_rn 0.5 ulp + one FMA: under 4e-4 px for |u| < 4096), and rint() of the two can only
-// differ when the estimate lies that close to a half-integer. Everything else -- non-finite values, large
-// magnitudes, near-ties (0.2 % of points) -- takes the exact path.
+// IEEE division is only paid when it can matter. The estimate num * rcp(|z|) + c (approximate reciprocal, 1 ulp,
+// plus one FMA rounding) is within |num/az| * 2^-22 + ulp(u) < 7e-4 px of the exactly rounded u for |u| < 2048, and
+// rint() of the two can only differ when the estimate lies that close to a half-integer. Everything else --
+// non-finite values, large magnitudes, near-ties (0.2 % of points) -- takes the exact path.
 __device__ __forceinline__ int project_px(float num, float az, float inv_az, float c, int cmax)
 {
     const float est = fmaf(num, inv_az, c);
-    const float fr = est - floorf(est);
-    if (fabsf(est) < 4096.f && fabsf(fr - 0.5f) > 1e-3f) {
-        const float r = rintf(est);
-        return r <= 0.f ? 0 : (r >= (float)cmax ? cmax : (int)r);
-    }
+    const float r = rintf(est);
+    if (fabsf(est) < 2048.f && fabsf(est - r) < 0.499f)                   // false for NaN
+        return (int)fminf(fmaxf(r, 0.f), (float)cmax);
     return round_clamp(__fadd_rn(__fdiv_rn(num, az), c), cmax);
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 template <int NT>
@@ -81,6 +86,7 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
     uint32_t* m16 = m4 + (size_t)H * Wp;            // [H * Wp]  OR of rows r .. r+15
     uint32_t* lat = m16 + (size_t)H * Wp;           // [2][n*n]  projected lattice plane: u | v << 16
     uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [2][dim*dim] (min2, max2) of a cell's 4 corners
+    float* axy = reinterpret_cast<float*>(quad + 2 * d2);                    // [3][n*n] the (x, y) part of cam = pose @ g2w @ p
     const uint8_t* D = depth + (size_t)view * H * W;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -130,18 +136,28 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
     const float p00 = P[0], p01 = P[1], p02 = P[2], p03 = P[3];
     const float p10 = P[4], p11 = P[5], p12 = P[6], p13 = P[7];
     const float p20 = P[8], p21 = P[9], p22 = P[10], p23 = P[11];
+    // cam = p0*wx + p1*wy + p2*wz + p3 is accumulated in that order (one FMA per term), so the first two terms do
+    // not depend on the plane: they are formed once per view with the same operations
+    {
+        const float rn = 1.0f / (float)n;
+        for (int q = tid; q < nn; q += NT) {
+            const int ly = (int)(((float)q + 0.5f) * rn), lx = q - ly * n;      // exact quotient for q < 2^20
+            // grid_to_world @ corner: inv*x + (-0.5)*1 (raytracing.py:35-40,64)
+            const float wx = __fadd_rn(__fmul_rn(inv_dim, (float)lx), -0.5f);
+            const float wy = __fadd_rn(__fmul_rn(inv_dim, (float)ly), -0.5f);
+            axy[q] = fmaf(p01, wy, __fmul_rn(p00, wx));
+            axy[nn + q] = fmaf(p11, wy, __fmul_rn(p10, wx));
+            axy[2 * nn + q] = fmaf(p21, wy, __fmul_rn(p20, wx));
+        }
+    }
     auto project_plane = [&](int lz, uint32_t* out) {
-        // grid_to_world @ corner: inv*x + (-0.5)*1 (raytracing.py:35-40,64)
         const float wz = __fadd_rn(__fmul_rn(inv_dim, (float)lz), -0.5f);
         for (int q = tid; q < nn; q += NT) {
-            int ly = q / n, lx = q - ly * n;
-            float wx = __fadd_rn(__fmul_rn(inv_dim, (float)lx), -0.5f);
-            float wy = __fadd_rn(__fmul_rn(inv_dim, (float)ly), -0.5f);
-            float camx = fmaf(p03, 1.f, fmaf(p02, wz, fmaf(p01, wy, __fmul_rn(p00, wx))));
-            float camy = fmaf(p13, 1.f, fmaf(p12, wz, fmaf(p11, wy, __fmul_rn(p10, wx))));
-            float camz = fmaf(p23, 1.f, fmaf(p22, wz, fmaf(p21, wy, __fmul_rn(p20, wx))));
+            const float camx = fmaf(p03, 1.f, fmaf(p02, wz, axy[q]));
+            const float camy = fmaf(p13, 1.f, fmaf(p12, wz, axy[nn + q]));
+            const float camz = fmaf(p23, 1.f, fmaf(p22, wz, axy[2 * nn + q]));
             const float az = fabsf(camz);
-            const float inv_az = __frcp_rn(az);
+            const float inv_az = rcp_approx(az);
             const int u = project_px(__fmul_rn(camx, focal), az, inv_az, cx, clamp_max);     // raytracing.py:71
             const int v = project_px(__fmul_rn(-camy, focal), az, inv_az, cy, clamp_max);    // :70,72
             out[q] = (uint32_t)u | ((uint32_t)v << 16);
@@ -156,14 +172,17 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
             out[q] = make_uint2(__vminu2(__vminu2(a, b), __vminu2(e, f)), __vmaxu2(__vmaxu2(a, b), __vmaxu2(e, f)));
         }
     };
+    __syncthreads();
     project_plane(z0, lat);
     __syncthreads();
     build_quads(lat, quad);
 
     // ---- 3. slice by slice: project plane z+1, then test the voxels between planes z and z+1
-    const long long nvox = (long long)d2 * dim;
-    const long long pw = (nvox + 31) >> 5;
+    const int nvox = d2 * dim;                      // dim <= 1023: fits
     const bool aligned = (d2 & 31) == 0;
+    uint32_t* const ow = occ_bits ? occ_bits + (size_t)view * ((nvox + 31) >> 5) : nullptr;
+    float* const of = occ_f32 ? occ_f32 + (size_t)view * nvox : nullptr;
+    long long* const im = index_map ? index_map + (size_t)view * 4 * nvox : nullptr;   // raytracing.py:76-80
     for (int z = z0; z < z1; ++z) {
         const int cur = (z - z0) & 1, nxt = cur ^ 1;
         project_plane(z + 1, lat + nxt * nn);
@@ -174,20 +193,20 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
         const uint2* qb = quad + nxt * d2;
         for (int base = tid - lane; base < d2; base += NT) {
             const int q = base + lane;
-            const bool valid = q < d2;
+            const int lin = z * d2 + q;
             bool occ = false;
-            const long long lin = (long long)z * d2 + q;
-            if (valid) {
+            if (q < d2) {
                 const uint2 A = qa[q], B = qb[q];
                 const uint32_t mn = __vminu2(A.x, B.x), mx = __vmaxu2(A.y, B.y);
-                const int umin = mn & 0xffffu, vmin = mn >> 16, umax = mx & 0xffffu, vmax = mx >> 16;
-                if (index_map) {
-                    long long* im = index_map + (long long)view * 4 * nvox + lin;   // raytracing.py:76-80
-                    im[0] = umin; im[nvox] = vmin; im[2 * nvox] = umax; im[3 * nvox] = vmax;
+                if (im) {
+                    im[lin] = mn & 0xffffu; im[nvox + lin] = mn >> 16;
+                    im[2 * (size_t)nvox + lin] = mx & 0xffffu; im[3 * (size_t)nvox + lin] = mx >> 16;
                 }
-                // depth[vmin:vmax, umin:umax] > 0 with numpy's end clipping (raytracing.py:134)
-                const int u0 = min(umin, W), u1 = min(umax, W);
-                const int v0 = min(vmin, H), v1 = min(vmax, H);
+                // depth[vmin:vmax, umin:umax] > 0 with numpy's end clipping (raytracing.py:134): clip both packed
+                // corners to (W, H) at once
+                const uint32_t lim = (uint32_t)W | ((uint32_t)H << 16);
+                const uint32_t lo = __vminu2(mn, lim), hi = __vminu2(mx, lim);
+                const int u0 = lo & 0xffffu, v0 = lo >> 16, u1 = hi & 0xffffu, v1 = hi >> 16;
                 if (depth && u1 > u0 && v1 > v0) {
                     const int wa = u0 >> 5, wb = (u1 - 1) >> 5;
                     const uint32_t ma = 0xffffffffu << (u0 & 31);
@@ -197,22 +216,21 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
                     const int nrow = v1 - v0;
                     const uint32_t* mk = nrow >= 16 ? m16 : (nrow >= 4 ? m4 : m1);
                     const int h = nrow >= 16 ? 16 : (nrow >= 4 ? 4 : 1);
+                    const uint32_t* last = mk + (v1 - h) * Wp;
                     uint32_t hit = 0;
                     for (int w = wa; w <= wb; ++w) {
-                        uint32_t acc = 0;
-                        for (int row = v0; row + h <= v1; row += h) acc |= mk[row * Wp + w];
-                        acc |= mk[(v1 - h) * Wp + w];
+                        uint32_t acc = last[w];
+                        for (const uint32_t* r = mk + v0 * Wp; r < last; r += h * Wp) acc |= r[w];
                         if (w == wa) acc &= ma;
                         if (w == wb) acc &= mb;
                         hit |= acc;
                     }
                     occ = hit != 0;
                 }
-                if (occ_f32) occ_f32[(long long)view * nvox + lin] = occ ? 1.f : 0.f;
+                if (of) of[lin] = occ ? 1.f : 0.f;
             }
             const uint32_t word = __ballot_sync(0xffffffffu, occ);
-            if (occ_bits) {
-                uint32_t* ow = occ_bits + (long long)view * pw;
+            if (ow) {
                 if (aligned) { if (lane == 0) ow[lin >> 5] = word; }
                 else if (occ) atomicOr(ow + (lin >> 5), 1u << (lin & 31));
             }
@@ -234,7 +252,8 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     if (!pose || (!depth && (occ_bits || occ_f32))) { set_error("raycast: null input"); return G3D_ERR_INVALID; }
     constexpr int NT = 512;
     const int n = dim + 1;
-    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 3 + ((size_t)2 * n * n + 1) * 4 + (size_t)2 * dim * dim * 8;
+    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 3 + ((size_t)2 * n * n + 1) * 4 + (size_t)2 * dim * dim * 8 +
+                        (size_t)3 * n * n * 4;
     if (smem > 227 * 1024) {
         set_error("raycast: image %dx%d needs %zu bytes of shared memory (max 232448)", H, W, smem);
         return G3D_ERR_INVALID;
