@@ -14,6 +14,8 @@
 //     arithmetic: cam = pose @ (g2w @ p) accumulated k = 0..3 with one FMA per
 //     term (the association MKL sgemm uses for raytracing.py:64, pinned by the
 //     golden fixtures), y flipped, u = x*f/|z| + cx, round-half-even, clamp.
+//     The first two terms of that sum do not depend on the plane and are formed
+//     once per view (3 floats per (x, y) lattice point in shared memory).
 //     Planes are projected one at a time and kept two at a time; per plane the
 //     4-corner min/max of every (x, y) cell is formed once with packed 16-bit
 //     SIMD min/max, so a voxel's box is two 8-byte loads and two instructions;
