@@ -9,11 +9,13 @@
 //                operation order), the double-precision grid coordinates, the band box
 //                [int(min)-b, int(max)+b+1] (cpp:131-137) and the x-ray intersection counts (cpp:147-160).
 //                Only the PARITY of the counts is ever used (cpp:178), so they are kept as XOR-ed bits.
-//  tdf_init      one warp / triangle over its band box. The reference's serial "if (d < phi) {phi = d;
-//                closest = t}" over t = 0..T-1 ends at (min d, lowest t attaining it); atomicMin on the 64-bit
-//                key (float_bits(d) << 32 | t) is exactly that, in any order. A node farther from the
-//                triangle's bounding box than its current phi cannot win and is dropped before the evaluation
-//                (9 in 10 are); survivors are compacted and evaluated 32 at a time.
+//  tdf_init      the band initialisation. The reference's serial "if (d < phi) {phi = d; closest = t}" over
+//                t = 0..T-1 ends at (min d, lowest t attaining it); atomicMin on the 64-bit key
+//                (float_bits(d) << 32 | t) is exactly that, in any order. A node farther from the triangle's
+//                bounding box than its current phi cannot win and is dropped before the evaluation (9 in 10
+//                are); survivors are compacted and evaluated 32 at a time. Two kernels: tiled (one CTA per
+//                16^3 block of a mesh, keys of the block in shared memory; batches of small grids) and scatter
+//                (one warp per triangle, keys in global memory; large grids, small batches).
 //  tdf_sweep     one CTA (or one thread-block cluster) / mesh, the 2 x 8 Gauss-Seidel sweeps (cpp:57-80,
 //                163-172). Within one sweep node (a,b,c) (sweep-relative) reads only nodes of smaller a+b+c,
 //                so the nodes of one anti-diagonal level are independent: 16 x (ni+nj+nk-5) synchronous
@@ -26,8 +28,8 @@
 //
 // Exact mode (g3d_tdf_exact.cuh) shares prep and finalize and replaces init + sweeps by a culled brute force.
 //
-// HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B; keys u64 [n_mesh, nk, nj, ni]
-// (hi = phi bits, lo = closest_tri); change bytes u8 [n_mesh, nvox]; parity bits u32 [n_mesh, ceil(nvox/32)];
+// HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B; keys u64 per mesh in 4x4x4 bricks
+// (hi = phi bits, lo = sweep change code << 27 | closest_tri; see KeyMap); parity bits u32 [n_mesh, ceil(nvox/32)];
 // sweep order table (shared by all meshes).
 #include <limits.h>
 #include <stdlib.h>
@@ -1049,7 +1051,7 @@ int tdf_validate(int32_t n_mesh, int64_t total_verts, int64_t total_tris, const 
 
 // The work of one batch call in four phases, so that the host-buffer front end can start on the first
 // triangles while the rest of the batch is still crossing PCIe:
-//   tdf_begin        validate, carve the workspace, initialise keys / parity / change bytes
+//   tdf_begin        validate, carve the workspace, initialise keys / parity
 //   tdf_stage_tris   per-triangle work for triangles [t0, t1): records, boxes, parity (+ band init, faithful mode)
 //   tdf_solve        the whole-batch part: sweeps, or the exact kernel
 //   tdf_finalize     the fused epilogue for meshes [m0, m1), so that results can start their way back per chunk

@@ -99,7 +99,8 @@ size_t g3d_tdf_workspace_bytes(int32_t n_mesh, int64_t total_verts, int64_t tota
  * tris      u32 [total_tris, 3]    vertex indices LOCAL to their mesh
  * tri_off   i64 [n_mesh + 1]       first triangle of each mesh
  * total_verts/total_tris repeat vert_off[n_mesh]/tri_off[n_mesh] so that the
- * host never has to read device memory.
+ * host never has to read device memory. At most 2^27 - 2 triangles per call
+ * (G3D_ERR_INVALID beyond; split the batch).
  */
 int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_verts,
                   const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
