@@ -196,6 +196,8 @@ def run_b200(args, rank, world, local):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # several ranks on one host: keep each rank's pinned buffers on its GPU's socket (G3D_NO_NUMA_BIND=1 disables)
+    numa = shard.bind_to_gpu_numa_node(local) if (world > 1 and not os.environ.get("G3D_NO_NUMA_BIND")) else None
     L = _lib.lib()
     peaks, peak_src = measured_peaks()
 
@@ -413,7 +415,8 @@ def run_b200(args, rank, world, local):
         e2e = {"value": total_vox / dt, "unit": "voxels/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(V.nbytes + T.nbytes + voff.nbytes + toff.nbytes),
                "d2h_bytes_per_step": int(hsdf.numel() * 4 + hbits.numel() * 4 + hstat.numel() * 4),
-               "api": "g3d_tdf_batch_host (pinned host buffers; outputs: sdf + occupancy bits + status)"}
+               "api": "g3d_tdf_batch_host (pinned host buffers; outputs: sdf + occupancy bits + status)",
+               "numa_bind": numa}
         L.g3d_context_destroy(ctx)
         tdf_launches += 6 * args.steps if args.mode == "faithful" else 4 * args.steps
 

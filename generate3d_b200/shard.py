@@ -22,6 +22,58 @@ def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _gpu_pci_address(device_index):
+    """'dddd:bb:dd.f' of a CUDA device as sysfs spells it, or None."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        return "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except (AttributeError, RuntimeError):
+        pass
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        return dom[-4:] + ":" + rest
+    except Exception:                                     # no NVML, no device: nothing to bind to
+        return None
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index, sysfs="/sys"):
+    """One process per GPU on a multi-socket host: run (and therefore first-touch and pin host buffers) on the
+    CPUs of the NUMA node the GPU hangs off, so that the host<->device copies of the host-buffer front end do not
+    cross the socket interconnect. Returns {'numa_node', 'cpus'} or None when the topology is unknown, the node
+    has no CPU this process may use, or the host has a single node. Never raises."""
+    try:
+        addr = _gpu_pci_address(device_index)
+        if addr is None:
+            return None
+        with open(os.path.join(sysfs, "bus/pci/devices", addr, "numa_node")) as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed or allowed == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except (OSError, ValueError):
+        return None
+
+
 def init_process_group(backend=None):
     """Initialise torch.distributed from the torchrun environment (no-op when single-process)."""
     rank, world, local = env_rank_world()

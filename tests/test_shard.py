@@ -54,3 +54,31 @@ def test_two_rank_gloo_shard_and_gather():
     for r, full, tmax, tsum in res:
         assert full == [float(i) for i in range(n_total)]
         assert tmax == 2.0 and tsum == n_total
+
+
+def test_bind_to_gpu_numa_node_with_fake_sysfs(tmp_path, monkeypatch):
+    """Topology lookup of the multi-GPU host path: PCI address -> numa_node -> cpulist -> sched_setaffinity;
+    unknown topology must come back as None, never as an exception."""
+    from generate3d_b200 import shard
+    have = sorted(os.sched_getaffinity(0))
+    monkeypatch.setattr(shard, "_gpu_pci_address", lambda i: "0000:1b:00.0")
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (dev / "numa_node").write_text("-1\n")
+    assert shard.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None            # single-node host
+    (dev / "numa_node").write_text("1\n")
+    (node / "cpulist").write_text("%d\n" % have[0])
+    calls = []
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: calls.append(set(cpus)))
+    got = shard.bind_to_gpu_numa_node(0, sysfs=str(tmp_path))
+    if len(have) > 1:
+        assert got == {"numa_node": 1, "cpus": 1} and calls == [{have[0]}]
+    else:
+        assert got is None and not calls                                          # nothing to narrow down
+    (node / "cpulist").write_text("100000-100003\n")                            # no usable CPU on that node
+    assert shard.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    monkeypatch.setattr(shard, "_gpu_pci_address", lambda i: None)
+    assert shard.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert shard._parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11}
