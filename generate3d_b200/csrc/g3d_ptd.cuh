@@ -122,8 +122,9 @@ __device__ __forceinline__ TriRec load_trirec(const float4* __restrict__ p)
     return r;
 }
 
-// point_segment_distance with the squared edge length supplied
-__device__ __forceinline__ float point_segment_distance_m2(V3 x0, V3 x1, V3 x2, float m2)
+// point_segment_distance with the squared edge length supplied, returning the SQUARED distance (the argument of
+// the final sqrt of vec.h:210-220)
+__device__ __forceinline__ float point_segment_dist2_m2(V3 x0, V3 x1, V3 x2, float m2)
 {
     V3 e = sub3(x2, x1);
     float s12 = __fdiv_rn(dot3(sub3(x2, x0), e), m2);
@@ -132,9 +133,13 @@ __device__ __forceinline__ float point_segment_distance_m2(V3 x0, V3 x1, V3 x2, 
     float om = sub(1.f, s12);
     V3 c = { add(mul(x1.x, s12), mul(x2.x, om)), add(mul(x1.y, s12), mul(x2.y, om)),
              add(mul(x1.z, s12), mul(x2.z, om)) };
-    return dist3(x0, c);
+    V3 t = sub3(x0, c);
+    return dot3(t, t);
 }
 
+// One square root per evaluation instead of up to two: the correctly rounded sqrt is non-decreasing, so
+// std::min(sqrt(q1), sqrt(q2)) == sqrt(std::min(q1, q2)) bit for bit, NaN operands included (both forms
+// keep the FIRST operand unless the second compares smaller).
 __device__ __forceinline__ float point_triangle_distance(V3 x0, const TriRec& t)
 {
     V3 x13 = sub3(t.x1, t.x3), x23 = sub3(t.x2, t.x3), x03 = sub3(x0, t.x3);
@@ -142,20 +147,24 @@ __device__ __forceinline__ float point_triangle_distance(V3 x0, const TriRec& t)
     float w23 = mul(t.invdet, sub(mul(t.m23, a), mul(t.d, b)));
     float w31 = mul(t.invdet, sub(mul(t.m13, b), mul(t.d, a)));
     float w12 = sub(sub(1.f, w23), w31);
+    float q2;
     if (w23 >= 0.f && w31 >= 0.f && w12 >= 0.f) {
         V3 c = { add(add(mul(t.x1.x, w23), mul(t.x2.x, w31)), mul(t.x3.x, w12)),
                  add(add(mul(t.x1.y, w23), mul(t.x2.y, w31)), mul(t.x3.y, w12)),
                  add(add(mul(t.x1.z, w23), mul(t.x2.z, w31)), mul(t.x3.z, w12)) };
-        return dist3(x0, c);
+        V3 e = sub3(x0, c);
+        q2 = dot3(e, e);
+    } else {
+        bool p = w23 > 0.f, q = w31 > 0.f;
+        V3 a2 = (p || q) ? t.x2 : t.x3;           // first segment x1-a2
+        float ma = (p || q) ? t.m2_12 : t.m2_13;
+        V3 b1 = p ? t.x1 : t.x2;                  // second segment b1-x3
+        float mb = p ? t.m2_13 : t.m2_23;
+        float s1 = point_segment_dist2_m2(x0, t.x1, a2, ma);
+        float s2 = point_segment_dist2_m2(x0, b1, t.x3, mb);
+        q2 = std_min(s1, s2);
     }
-    bool p = w23 > 0.f, q = w31 > 0.f;
-    V3 a2 = (p || q) ? t.x2 : t.x3;           // first segment x1-a2
-    float ma = (p || q) ? t.m2_12 : t.m2_13;
-    V3 b1 = p ? t.x1 : t.x2;                  // second segment b1-x3
-    float mb = p ? t.m2_13 : t.m2_23;
-    float s1 = point_segment_distance_m2(x0, t.x1, a2, ma);
-    float s2 = point_segment_distance_m2(x0, b1, t.x3, mb);
-    return std_min(s1, s2);
+    return __fsqrt_rn(q2);
 }
 
 // (int)x the way x86-64 cvttsd2si does it: NaN / out of range -> INT_MIN.
