@@ -18,7 +18,9 @@
 //     once per view (3 floats per (x, y) lattice point in shared memory).
 //     Planes are projected one at a time and kept two at a time; per plane the
 //     4-corner min/max of every (x, y) cell is formed once with packed 16-bit
-//     SIMD min/max, so a voxel's box is two 8-byte loads and two instructions;
+//     SIMD min/max by the thread that owns the cell in every slice, which keeps
+//     the previous plane's value for itself: a voxel's box is that value, four
+//     lattice loads and eight packed min/max, and a slice needs one barrier;
 //  3. each voxel tests its box against the coarsest fitting mask in at most 4 reads (half-open,
 //     clipped to the image as numpy slicing does); a warp ballots 32 voxels
 //     into one output word, so the bit-packed grid is written without atomics.
@@ -87,8 +89,8 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
     uint32_t* m4 = m1 + (size_t)H * Wp;             // [H * Wp]  OR of rows r .. r+3
     uint32_t* m16 = m4 + (size_t)H * Wp;            // [H * Wp]  OR of rows r .. r+15
     uint32_t* lat = m16 + (size_t)H * Wp;           // [2][n*n]  projected lattice plane: u | v << 16
-    uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [2][dim*dim] (min2, max2) of a cell's 4 corners
-    float* axy = reinterpret_cast<float*>(quad + 2 * d2);                    // [3][n*n] the (x, y) part of cam = pose @ g2w @ p
+    uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [dim*dim] (min2, max2) of a cell's 4 corners in the previous plane
+    float* axy = reinterpret_cast<float*>(quad + d2);                    // [3][n*n] the (x, y) part of cam = pose @ g2w @ p
     const uint8_t* D = depth + (size_t)view * H * W;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -165,19 +167,19 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
             out[q] = (uint32_t)u | ((uint32_t)v << 16);
         }
     };
-    auto build_quads = [&](const uint32_t* in, uint2* out) {
-        // per cell (x, y) of the plane: packed (umin | vmin << 16, umax | vmax << 16) over its 4 corners
-        for (int q = tid; q < d2; q += NT) {
-            int y = q / dim, x = q - y * dim;
-            const uint32_t* c = in + y * n + x;
-            uint32_t a = c[0], b = c[1], e = c[n], f = c[n + 1];
-            out[q] = make_uint2(__vminu2(__vminu2(a, b), __vminu2(e, f)), __vmaxu2(__vmaxu2(a, b), __vmaxu2(e, f)));
-        }
+    // per cell (x, y) of a plane: packed (umin | vmin << 16, umax | vmax << 16) over its 4 corners. A cell is
+    // always handled by the same thread (slice after slice), so the previous plane's value needs no barrier.
+    const float rdim = 1.0f / (float)dim;
+    auto cell_quad = [&](const uint32_t* in, int q) {
+        const int y = (int)(((float)q + 0.5f) * rdim), x = q - y * dim;          // exact quotient for q < 2^20
+        const uint32_t* c = in + y * n + x;
+        const uint32_t a = c[0], b = c[1], e = c[n], f = c[n + 1];
+        return make_uint2(__vminu2(__vminu2(a, b), __vminu2(e, f)), __vmaxu2(__vmaxu2(a, b), __vmaxu2(e, f)));
     };
     __syncthreads();
     project_plane(z0, lat);
     __syncthreads();
-    build_quads(lat, quad);
+    for (int q = tid; q < d2; q += NT) quad[q] = cell_quad(lat, q);
 
     // ---- 3. slice by slice: project plane z+1, then test the voxels between planes z and z+1
     const int nvox = d2 * dim;                      // dim <= 1023: fits
@@ -188,17 +190,15 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
     for (int z = z0; z < z1; ++z) {
         const int cur = (z - z0) & 1, nxt = cur ^ 1;
         project_plane(z + 1, lat + nxt * nn);
-        __syncthreads();                            // plane z+1 projected; everyone is done with slice z-1
-        build_quads(lat + nxt * nn, quad + nxt * d2);
-        __syncthreads();
-        const uint2* qa = quad + cur * d2;
-        const uint2* qb = quad + nxt * d2;
+        __syncthreads();                            // plane z+1 projected; plane z-1's buffer is free again
+        const uint32_t* lnx = lat + nxt * nn;
         for (int base = tid - lane; base < d2; base += NT) {
             const int q = base + lane;
             const int lin = z * d2 + q;
             bool occ = false;
             if (q < d2) {
-                const uint2 A = qa[q], B = qb[q];
+                const uint2 A = quad[q], B = cell_quad(lnx, q);
+                quad[q] = B;
                 const uint32_t mn = __vminu2(A.x, B.x), mx = __vmaxu2(A.y, B.y);
                 if (im) {
                     im[lin] = mn & 0xffffu; im[nvox + lin] = mn >> 16;
@@ -254,7 +254,7 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     if (!pose || (!depth && (occ_bits || occ_f32))) { set_error("raycast: null input"); return G3D_ERR_INVALID; }
     constexpr int NT = 512;
     const int n = dim + 1;
-    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 3 + ((size_t)2 * n * n + 1) * 4 + (size_t)2 * dim * dim * 8 +
+    const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 3 + ((size_t)2 * n * n + 1) * 4 + (size_t)dim * dim * 8 +
                         (size_t)3 * n * n * 4;
     if (smem > 227 * 1024) {
         set_error("raycast: image %dx%d needs %zu bytes of shared memory (max 232448)", H, W, smem);
