@@ -72,25 +72,29 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
-template <int NT>
+// DIM > 0: grid size known at compile time (the reference only ever uses 32): the shared-memory layout and the
+// index arithmetic of the inner loops fold into immediates. DIM = 0: any size, from the `dim_arg` argument.
+template <int NT, int DIM>
 __global__ void __launch_bounds__(NT, 3)
 raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose, int H, int W,
-               float focal, float cx, float cy, int clamp_max, int dim, int zs, float inv_dim,
+               float focal, float cx, float cy, int clamp_max, int dim_arg, int zs, float inv_dim,
                uint32_t* __restrict__ occ_bits, float* __restrict__ occ_f32,
                long long* __restrict__ index_map)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int view = blockIdx.x;
     const int z0 = blockIdx.y * zs;
-    const int z1 = min(dim, z0 + zs);
+    const int z1 = min(DIM ? DIM : dim_arg, z0 + zs);
     const int Wp = (W + 31) >> 5;
+    const int dim = DIM ? DIM : dim_arg;
     const int n = dim + 1, nn = n * n, d2 = dim * dim;
-    uint32_t* m1 = smem;                            // [H * Wp]  depth > 0, one bit per pixel
+    // fixed-size arrays first, so that their offsets do not depend on the image size
+    uint32_t* lat = smem;                           // [2][n*n]  projected lattice plane: u | v << 16
+    uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [dim*dim] (min2, max2) of a cell's 4 corners in the previous plane
+    float* axy = reinterpret_cast<float*>(quad + d2);                        // [3][n*n] the (x, y) part of cam = pose @ g2w @ p
+    uint32_t* m1 = reinterpret_cast<uint32_t*>(axy + 3 * nn + ((3 * nn) & 1));   // [H * Wp]  depth > 0, one bit per pixel
     uint32_t* m4 = m1 + (size_t)H * Wp;             // [H * Wp]  OR of rows r .. r+3
     uint32_t* m16 = m4 + (size_t)H * Wp;            // [H * Wp]  OR of rows r .. r+15
-    uint32_t* lat = m16 + (size_t)H * Wp;           // [2][n*n]  projected lattice plane: u | v << 16
-    uint2* quad = reinterpret_cast<uint2*>(lat + 2 * nn + ((2 * nn) & 1));   // [dim*dim] (min2, max2) of a cell's 4 corners in the previous plane
-    float* axy = reinterpret_cast<float*>(quad + d2);                    // [3][n*n] the (x, y) part of cam = pose @ g2w @ p
     const uint8_t* D = depth + (size_t)view * H * W;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -255,7 +259,7 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     constexpr int NT = 512;
     const int n = dim + 1;
     const size_t smem = (size_t)H * ((W + 31) / 32) * 4 * 3 + ((size_t)2 * n * n + 1) * 4 + (size_t)dim * dim * 8 +
-                        (size_t)3 * n * n * 4;
+                        ((size_t)3 * n * n + 1) * 4 + 16;
     if (smem > 227 * 1024) {
         set_error("raycast: image %dx%d needs %zu bytes of shared memory (max 232448)", H, W, smem);
         return G3D_ERR_INVALID;
@@ -265,13 +269,14 @@ int raycast_launch(const uint8_t* depth, const float* pose, int32_t n_view, int3
     int zs = dim;
     const int target = 2 * sm_count();
     while (zs > 1 && (int64_t)n_view * ((dim + zs - 1) / zs) < target) zs = (zs + 1) / 2;
-    G3D_CUDA_TRY(cudaFuncSetAttribute(raycast_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = dim == 32 ? raycast_kernel<NT, 32> : raycast_kernel<NT, 0>;
+    G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nvox = (int64_t)dim * dim * dim;
     if (occ_bits && ((dim * dim) & 31))
         G3D_CUDA_TRY(cudaMemsetAsync(occ_bits, 0, (size_t)n_view * ((nvox + 31) / 32) * 4, stream));
     dim3 grid((unsigned)n_view, (unsigned)((dim + zs - 1) / zs));
     prof_begin(stream);
-    raycast_kernel<NT><<<grid, NT, smem, stream>>>(depth, pose, H, W, focal, cx, cy, clamp_max, dim, zs,
+    kern<<<grid, NT, smem, stream>>>(depth, pose, H, W, focal, cx, cy, clamp_max, dim, zs,
                                                    1.0f / (float)dim, occ_bits, occ_f32,
                                                    reinterpret_cast<long long*>(index_map));
     prof_mark(ST_RAYCAST, stream);
