@@ -224,12 +224,23 @@ raycast_kernel(const uint8_t* __restrict__ depth, const float* __restrict__ pose
                     const int h = nrow >= 16 ? 16 : (nrow >= 4 ? 4 : 1);
                     const uint32_t* last = mk + (v1 - h) * Wp;
                     uint32_t hit = 0;
-                    for (int w = wa; w <= wb; ++w) {
-                        uint32_t acc = last[w];
-                        for (const uint32_t* r = mk + v0 * Wp; r < last; r += h * Wp) acc |= r[w];
-                        if (w == wa) acc &= ma;
-                        if (w == wb) acc &= mb;
-                        hit |= acc;
+                    if (wb - wa <= 1 && nrow <= 4 * h) {
+                        // the usual case (a voxel covers a few pixels): at most four windows and two words,
+                        // read without loops; windows past the last one are clamped onto it
+                        const uint32_t* r0 = mk + v0 * Wp;
+                        const uint32_t* r1 = mk + min(v0 + h, v1 - h) * Wp;
+                        const uint32_t* r2 = mk + min(v0 + 2 * h, v1 - h) * Wp;
+                        const uint32_t a = (r0[wa] | r1[wa] | r2[wa] | last[wa]) & ma;
+                        const uint32_t b = (r0[wb] | r1[wb] | r2[wb] | last[wb]) & mb;
+                        hit = wa == wb ? (a & b) : (a | b);     // one word: both edge masks apply to it
+                    } else {
+                        for (int w = wa; w <= wb; ++w) {
+                            uint32_t acc = last[w];
+                            for (const uint32_t* r = mk + v0 * Wp; r < last; r += h * Wp) acc |= r[w];
+                            if (w == wa) acc &= ma;
+                            if (w == wb) acc &= mb;
+                            hit |= acc;
+                        }
                     }
                     occ = hit != 0;
                 }
