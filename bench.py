@@ -353,7 +353,7 @@ def run_b200(args, rank, world, local):
                      "bytes_per_view": bytes_per_view,
                      "traffic": (traffic_table().get("raycast_kernel", {}).get("bytes_per_view", 0) * nview_b) or None,
                      "issue_active_pct": traffic_table().get("raycast_kernel", {}).get("issue_active_pct"),
-                     "note": "ALU-bound: ~210 k warp instructions per view against 70 KB of traffic; the HBM fraction is reported because the metric asks for it"},
+                     "note": "ALU-bound: ~213 k warp instructions per view against 70 KB of traffic; the HBM fraction is reported because the metric asks for it"},
     }
     ray_launches = max(args.steps, 20) + args.steps
 
