@@ -386,7 +386,16 @@ def run_b200(args, rank, world, local):
             "raycast_color": {"value": world * 20 * 512 * 512 / (ms_col * 1e-3), "unit": "rays/s", "ms_per_step": ms_col,
                               "workload": "20 views 512x512 colour + depth -> 32^3 mean-colour grids (raytracing.raycast)"},
         }
-        ray_launches += 2 * (max(args.steps, 10) + 3)
+        # z-buffered index maps of the projection layer: 16 GT grids x 20 views at 512^2
+        from generate3d_b200 import perspective_projection as pp
+        helper = pp.ProjectionHelper(dev)
+        zl = torch.where(occ_in[:16] > 0, 4.0, -4.0)
+        zp = dp512.reshape(1, 20, 4, 4).expand(16, 20, 4, 4).contiguous()
+        ms_zb = timed(lambda: helper.index_mapping_batch_n_views(zl, zp), max(args.steps, 10))
+        next_rows["zbuffer_index_map"] = {
+            "value": world * 16 * 20 * 512 * 512 / (ms_zb * 1e-3), "unit": "pixels/s", "ms_per_step": ms_zb,
+            "workload": "16 GT occupancy grids x 20 views 512x512 -> voxel index per pixel (ProjectionHelper.index_mapping_batch_n_views)"}
+        ray_launches += 2 * (max(args.steps, 10) + 3) + 2 * (max(args.steps, 10) + 3)
 
     # ---- e2e through the host-buffer C ABI: pinned host arrays in, sdf + occupancy bits + status out
     e2e = None

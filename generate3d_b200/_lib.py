@@ -56,6 +56,7 @@ SYMBOLS = {
     "g3d_raycast_color_batch": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _i32, _vp, _vp]),
     "g3d_raymarch": (C.c_int, [_vp, _vp, _i32, _i32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i32,
                                _vp, _vp, _vp, _vp]),
+    "g3d_zbuffer_index_map": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, C.c_float, C.c_float, C.c_float, _i32, _i32, _vp, _vp]),
     "g3d_profile_enable": (C.c_int, [_i32]),
     "g3d_profile_read": (C.c_int, [_vp, _vp]),
     "g3d_probe_fp32_tflops": (C.c_int, [_vp, _vp]),

@@ -248,3 +248,105 @@ extern "C" int g3d_raymarch(const uint8_t* depth, const uint8_t* color, int32_t 
     G3D_CUDA_TRY(cudaGetLastError());
     return G3D_OK;
 }
+
+// ------------------------------------------------------------------ z-buffered index map ----
+// Network/perspective_projection.py:65-128 (ProjectionHelper.compute_index_mapping): every occupied voxel is
+// projected (8 corners, pixel bounding box half-open as numpy slices it, depth = min |z_cam| of the corners) and
+// painted into the image in increasing voxel order, a pixel changing hands only for a strictly smaller depth.
+// The result per pixel is therefore the minimum of (depth, voxel index) over the voxels whose box covers it --
+// an atomicMin on depth_bits << 32 | index, in any order. The int64 output doubles as the key buffer.
+#include "g3d_project.cuh"
+
+namespace g3d {
+namespace {
+
+__global__ void __launch_bounds__(256)
+zbuffer_paint_kernel(const uint32_t* __restrict__ occ_bits, const float* __restrict__ pose, int n_view, int H, int W,
+                     float focal, float cx, float cy, int clamp_max, int dim, float inv_dim,
+                     unsigned long long* __restrict__ key)
+{
+    const int gv = blockIdx.y;                                  // grid * n_view + view
+    const int grid = gv / n_view;
+    const int nvox = dim * dim * dim;
+    const uint32_t* bits = occ_bits + (size_t)grid * ((nvox + 31) >> 5);
+    const float* P = pose + (size_t)gv * 16;
+    unsigned long long* K = key + (size_t)gv * H * W;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int w0 = warp; w0 < (nvox + 31) >> 5; w0 += nwarp) {
+        uint32_t m = __ldg(bits + w0);
+        while (m) {
+            const int lin = (w0 << 5) + __ffs(m) - 1;           // lin = x + dim*(y + dim*z) (perspective_projection.py:78-84)
+            m &= m - 1;
+            if (lin >= nvox) break;
+            const int z = lin / (dim * dim), r = lin - z * dim * dim, y = r / dim, x = r - y * dim;
+            // lanes 0..7 project one corner each (vertex_coords, :88-91: bit 0 -> x, bit 1 -> y, bit 2 -> z)
+            const int c = lane & 7;
+            const float wx = __fadd_rn(__fmul_rn(inv_dim, (float)(x + (c & 1))), -0.5f);
+            const float wy = __fadd_rn(__fmul_rn(inv_dim, (float)(y + ((c >> 1) & 1))), -0.5f);
+            const float wz = __fadd_rn(__fmul_rn(inv_dim, (float)(z + (c >> 2))), -0.5f);
+            // pose @ (grid_to_world @ corner), accumulated k = 0..3 with one FMA per term (as in g3d_raycast.cu)
+            const float camx = fmaf(P[3], 1.f, fmaf(P[2], wz, fmaf(P[1], wy, __fmul_rn(P[0], wx))));
+            const float camy = fmaf(P[7], 1.f, fmaf(P[6], wz, fmaf(P[5], wy, __fmul_rn(P[4], wx))));
+            const float camz = fmaf(P[11], 1.f, fmaf(P[10], wz, fmaf(P[9], wy, __fmul_rn(P[8], wx))));
+            const float az = fabsf(camz);
+            const float inv_az = rcp_approx(az);
+            int u = project_px(__fmul_rn(camx, focal), az, inv_az, cx, clamp_max);          // :104-110
+            int v = project_px(__fmul_rn(-camy, focal), az, inv_az, cy, clamp_max);
+            int umin = u, umax = u, vmin = v, vmax = v;
+            float depth = az;                                    // torch.min over the 8 corners (:98) propagates NaN
+            bool bad = !(az == az);
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, d)); umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, d));
+                vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d)); vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+                const float o = __shfl_xor_sync(0xffffffffu, depth, d);
+                depth = o < depth ? o : depth;
+                bad |= __shfl_xor_sync(0xffffffffu, (int)bad, d) != 0;
+            }
+            if (bad) continue;                                   // a NaN depth compares false everywhere: the voxel is never painted
+            const int u0 = min(umin, W), u1 = min(umax, W), v0 = min(vmin, H), v1 = min(vmax, H);   // slice end clipping
+            const int bw = u1 - u0, bh = v1 - v0;
+            if (bw <= 0 || bh <= 0) continue;
+            const unsigned long long k = ((unsigned long long)__float_as_uint(depth) << 32) | (uint32_t)lin;
+            for (int q = lane; q < bw * bh; q += 32) {
+                const int pv = v0 + q / bw, pu = u0 + q - (q / bw) * bw;
+                atomicMin(K + (size_t)pv * W + pu, k);
+            }
+        }
+    }
+}
+
+__global__ void zbuffer_resolve_kernel(long long* __restrict__ index_map, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = (unsigned long long)index_map[i];
+    index_map[i] = (k == ~0ull) ? -1ll : (long long)(uint32_t)k;  // :121-126
+}
+
+}  // namespace
+}  // namespace g3d
+
+extern "C" int g3d_zbuffer_index_map(const uint32_t* occ_bits, const float* pose, int32_t n_grid, int32_t n_view,
+                                     int32_t H, int32_t W, float focal, float cx, float cy, int32_t clamp_max,
+                                     int32_t dim, int64_t* index_map, void* cuda_stream)
+{
+    if (n_grid < 0 || n_view < 0 || H < 1 || W < 1 || dim < 1 || dim > 1023 || clamp_max < 0 || clamp_max > 65535) {
+        set_error("zbuffer_index_map: bad arguments (n_grid=%d n_view=%d H=%d W=%d dim=%d clamp_max=%d)", n_grid, n_view, H, W, dim, clamp_max);
+        return G3D_ERR_INVALID;
+    }
+    if (n_grid == 0 || n_view == 0) return G3D_OK;
+    if (!occ_bits || !pose || !index_map) { set_error("zbuffer_index_map: NULL pointer"); return G3D_ERR_INVALID; }
+    if ((int64_t)n_grid * n_view > 65535) { set_error("zbuffer_index_map: at most 65535 (grid, view) pairs per call"); return G3D_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t n = (size_t)n_grid * n_view * H * W;
+    G3D_CUDA_TRY(cudaMemsetAsync(index_map, 0xff, n * 8, s));   // all ones: "no voxel yet", and -1 once resolved
+    const int nword = (dim * dim * dim + 31) / 32;
+    dim3 grid((unsigned)((nword + 7) / 8 < 64 ? (nword + 7) / 8 : 64), (unsigned)(n_grid * n_view));
+    zbuffer_paint_kernel<<<grid, 256, 0, s>>>(occ_bits, pose, n_view, H, W, focal, cx, cy, clamp_max, dim,
+                                              1.0f / (float)dim, reinterpret_cast<unsigned long long*>(index_map));
+    zbuffer_resolve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<long long*>(index_map), n);
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}

@@ -28,6 +28,7 @@
 // Roofline: HBM. Algorithmic bytes per view = H*W (depth, read once) + 64
 // (pose) + dim^3/8 (packed occupancy) = 69,696 B at 256^2, 266,304 B at 512^2.
 #include "g3d_internal.h"
+#include "g3d_project.cuh"
 
 namespace g3d {
 
@@ -38,38 +39,6 @@ __device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w)
     // one bit per non-zero byte of w, in byte order
     uint32_t m = __vcmpne4(w, 0u) & 0x08040201u;
     return (m | (m >> 8) | (m >> 16) | (m >> 24)) & 0xfu;
-}
-
-// torch.round(p).long() then clamp(0, cmax) (raytracing.py:73-75). A NaN/inf/huge
-// float converts to INT64_MIN on x86-64, which the clamp turns into 0.
-__device__ __forceinline__ int round_clamp(float p, int cmax)
-{
-    float r = rintf(p);
-    if (!(fabsf(r) < 9.2e18f)) return 0;
-    if (r <= 0.f) return 0;
-    if (r >= (float)cmax) return cmax;
-    return (int)r;
-}
-
-// u = (x*f)/|z| + c rounded half-to-even and clamped, as the reference computes it (raytracing.py:71-75), but the
-// IEEE division is only paid when it can matter. The estimate num * rcp(|z|) + c (approximate reciprocal, 1 ulp,
-// plus one FMA rounding) is within |num/az| * 2^-22 + ulp(u) < 7e-4 px of the exactly rounded u for |u| < 2048, and
-// rint() of the two can only differ when the estimate lies that close to a half-integer. Everything else --
-// non-finite values, large magnitudes, near-ties (0.2 % of points) -- takes the exact path.
-__device__ __forceinline__ int project_px(float num, float az, float inv_az, float c, int cmax)
-{
-    const float est = fmaf(num, inv_az, c);
-    const float r = rintf(est);
-    if (fabsf(est) < 2048.f && fabsf(est - r) < 0.499f)                   // false for NaN
-        return (int)fminf(fmaxf(r, 0.f), (float)cmax);
-    return round_clamp(__fadd_rn(__fdiv_rn(num, az), c), cmax);
-}
-
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
 }
 
 // DIM > 0: grid size known at compile time (the reference only ever uses 32): the shared-memory layout and the

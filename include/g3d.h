@@ -198,6 +198,17 @@ int g3d_raymarch(const uint8_t* depth, const uint8_t* color, int32_t H, int32_t 
                  double focal, double z_near, double z_far, int32_t dim, uint8_t* occ, uint8_t* rgb,
                  uint32_t* scratch, void* cuda_stream);
 
+/* Z-buffered voxel -> pixel index map of the projection layer
+ * (Network/perspective_projection.py:65-128, ProjectionHelper.compute_index_mapping): for every pixel the linear
+ * index lin = x + dim*(y + dim*z) of the occupied voxel nearest to the camera among those whose projected box
+ * covers it (depth = min |z_cam| over the 8 corners, ties to the lower index), -1 where there is none.
+ * occ_bits u32 [n_grid, ceil(dim^3/32)] (bit lin&31 of word lin>>5; the reference's sigmoid(occ) > 0.2 mask),
+ * pose f32 [n_grid, n_view, 16], index_map i64 [n_grid, n_view, H*W]. Device pointers; no workspace (the
+ * output doubles as the key buffer). */
+int g3d_zbuffer_index_map(const uint32_t* occ_bits, const float* pose, int32_t n_grid, int32_t n_view,
+                          int32_t H, int32_t W, float focal, float cx, float cy, int32_t clamp_max,
+                          int32_t dim, int64_t* index_map, void* cuda_stream);
+
 /* ------------------------------------------------------------ profiling ----
  * Off by default. flags bit 0: record a CUDA event on the caller's stream between the kernels
  * of each g3d_tdf_batch / g3d_raycast_batch call (bench.py's per-kernel timing);

@@ -103,3 +103,51 @@ def test_txt_to_mesh_ply_bytes(golden_dir, tmp_path):
     (tmp_path / "g.txt").write_bytes(bytes(z["txt"]))
     voxel_grid.txt_to_mesh(str(tmp_path / "g.txt"), str(tmp_path / "g.ply"))
     assert (tmp_path / "g.ply").read_bytes() == bytes(z["ply"])
+
+
+def test_zbuffer_index_map_oracle_vs_reference(oracle, golden_dir):
+    """Projection layer's z-buffered index map (Network/perspective_projection.py:65-128): the numpy restatement
+    against the reference's own output on 3 grids x 3 poses (tests/golden/make_golden_projection.py)."""
+    z = np.load(os.path.join(golden_dir, "projection.npz"))
+    for g in range(z["logits"].shape[0]):
+        mask = 1.0 / (1.0 + np.exp(-z["logits"][g].astype(np.float64))) > 0.2
+        for q in range(z["poses"].shape[1]):
+            got = oracle.zbuffer_index_map(mask, z["poses"][g, q])
+            assert np.array_equal(got, z["index_map"][g, q].astype(np.int64)), (g, q)
+    assert (z["index_map"][2] == -1).all()                                    # empty grid: no pixel is hit
+
+
+@pytest.mark.gpu
+def test_zbuffer_index_map_gpu_vs_reference(g3d, oracle, golden_dir):
+    """ProjectionHelper drop-in: batch, n-view and single-view entry points against the reference's maps and
+    projected images, plus random occupancy / random poses against the oracle (ties in depth between voxels
+    sharing their nearest corner are the rule, not the exception)."""
+    from generate3d_b200 import perspective_projection as pp
+    z = np.load(os.path.join(golden_dir, "projection.npz"))
+    helper = pp.ProjectionHelper()
+    logits = torch.from_numpy(z["logits"]).cuda().unsqueeze(1)                # [B,1,D,H,W]
+    poses = torch.from_numpy(z["poses"]).cuda()
+    maps, projs = helper.project_batch_n_views(logits, poses)
+    assert maps.dtype == torch.int64 and tuple(maps.shape) == (3, 3, 512 * 512)
+    assert np.array_equal(maps.cpu().numpy(), z["index_map"].astype(np.int64))
+    assert np.array_equal(projs.cpu().numpy().view(np.uint32), z["proj"].view(np.uint32))
+    one = helper.compute_index_mapping(logits[0], poses[0, 1])
+    assert np.array_equal(one.cpu().numpy(), z["index_map"][0, 1])
+    nv = helper.index_mapping_n_views(logits[1], poses[1])
+    assert np.array_equal(nv.cpu().numpy(), z["index_map"][1])
+    # random grids and poses (camera far, near and inside the grid)
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        occ = rng.uniform(size=(32, 32, 32)) < (0.002, 0.02, 0.2, 0.6)[trial]
+        rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        p = np.eye(4, dtype=np.float32)
+        p[:3, :3] = rot
+        p[:3, 3] = [rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), -(2.0, 1.4, 0.9, 0.3)[trial]]
+        lg = torch.from_numpy(np.where(occ, 3.0, -3.0).astype(np.float32)).cuda()
+        got = helper.compute_index_mapping(lg, torch.from_numpy(p)).cpu().numpy()
+        assert np.array_equal(got, oracle.zbuffer_index_map(occ, p)), trial
+    # gradient scatter keeps the reference's shape contract
+    g = helper.copy_grad_n_views_occ(maps[0], torch.ones_like(projs[0]))
+    assert tuple(g.shape) == (32 ** 3,)
+    L = g3d.lib()
+    assert L.g3d_zbuffer_index_map(None, None, 1, 1, 512, 512, 525.0, 256.0, 256.0, 511, 32, None, None) == -1
