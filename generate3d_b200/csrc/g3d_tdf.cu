@@ -665,6 +665,9 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 //      pushes them into a private shared-memory queue, evaluates the queue densely (one pair
 //      per lane), and the owners then replay the results in neighbour order.
 constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
+// (three rounds need a 196 KB shared-memory carve-out at 7 CTAs per SM and lose more L1 than they gain: 13.8 ms
+// against 12.5 with two and 13.0 with one)
+__host__ __device__ constexpr int sweep_rounds(int nt) { return nt <= 256 ? 2 : 1; }   // rounds of a level sharing one queue
 constexpr uint32_t kTriMask = 0x7ffffffu;           // low 27 bits of a key's low word: closest_tri (all ones = none)
 
 __device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
@@ -700,13 +703,14 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     __shared__ int s_tmin[16];                      // smallest s_thr over the slots and the classes present in sweep s
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* q_tri = s_mem + lev_words + warp * (2 * kSweepQueue);
-    uint32_t* q_pos = q_tri + kSweepQueue;
-    // q_pos[e] is replaced by the pair's result (by the lane that read it). Shared memory is worth saving
-    // here: what the CTAs of an SM do not take stays L1, and the sweep lives on L1 hits (measured, 1,024 meshes:
-    // 14.0 ms with the default carve-out, 28 ms with the L1 squeezed to its minimum).
+    constexpr int R = sweep_rounds(NT);
+    uint32_t* q_tri = s_mem + lev_words + warp * (2 * R * kSweepQueue);
+    uint32_t* q_pos = q_tri + R * kSweepQueue;
+    // q_pos[e] is replaced by the pair's result (by the lane that read it). Shared memory is worth saving here:
+    // what the CTAs of an SM do not take stays L1 (measured, 1,024 meshes: flat up to a 164 KB carve-out with the
+    // bricked keys, +9 % at 196 KB, +100 % with the L1 squeezed to its minimum).
     // s_dirty[d][L]: newest change code among the upwind neighbours of the nodes of level L in direction d
-    uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * kSweepQueue));   // [8][nlev]
+    uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev]
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
     for (int l = threadIdx.x; l < 8 * nlev; l += NT) s_dirty[l] = 0;
     for (int e = threadIdx.x; e < 16 * 7 * 27; e += NT) {
@@ -762,11 +766,11 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
             // reference would make here is known to fail. (Cluster variant: the table is per CTA, no skipping.)
             if (!CL && (int)dirty[L] <= tmin) continue;
             const int beg = s_lev[L], end = s_lev[L + 1];
-            for (int qb = beg + crank * NT + warp * 32; qb < end; qb += NT * csize) {
-                const int q = qb + lane;
-                int c0 = -1, c1 = -1, c2 = -1, c3 = -1, c4 = -1, c5 = -1, c6 = -1, ct = -1, n = 0;
-                uint32_t need = 0, pos = 0;
-                float phi = 0.f;
+            // node phase of one round: candidates of this lane's node go to the queue from slot `qbase` on; returns
+            // the number of pairs the warp queued (warp-uniform)
+            auto node_phase = [&](int q, int qbase, uint32_t& need, uint32_t& pos, float& phi, int& ct, int& n, int& off) -> int {
+                int c0 = -1, c1 = -1, c2 = -1, c3 = -1, c4 = -1, c5 = -1, c6 = -1;
+                need = 0; pos = 0; phi = 0.f; ct = -1; n = 0; off = 0;
                 if (q < end) {
                     uint32_t o = __ldg(order + q);
                     int a = o & 1023, b = (o >> 10) & 1023, c = o >> 20;
@@ -810,7 +814,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                         if (need & 64u) prefetch_l1(T + 4 * (int64_t)c6);
                     }
                 }
-                if (!__any_sync(0xffffffffu, need != 0)) continue;
+                if (!__any_sync(0xffffffffu, need != 0)) return 0;
                 // warp-exclusive prefix of the per-lane work counts
                 const int cnt = __popc(need);
                 int incl = cnt;
@@ -819,18 +823,57 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     int v = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += v;
                 }
-                const int W = __shfl_sync(0xffffffffu, incl, 31);
-                const int off = incl - cnt;
-                {
-                    int w = off;
-                    if (need & 1u)  { q_tri[w] = c0; q_pos[w] = pos; ++w; }
-                    if (need & 2u)  { q_tri[w] = c1; q_pos[w] = pos; ++w; }
-                    if (need & 4u)  { q_tri[w] = c2; q_pos[w] = pos; ++w; }
-                    if (need & 8u)  { q_tri[w] = c3; q_pos[w] = pos; ++w; }
-                    if (need & 16u) { q_tri[w] = c4; q_pos[w] = pos; ++w; }
-                    if (need & 32u) { q_tri[w] = c5; q_pos[w] = pos; ++w; }
-                    if (need & 64u) { q_tri[w] = c6; q_pos[w] = pos; ++w; }
+                off = qbase + incl - cnt;
+                int w = off;
+                if (need & 1u)  { q_tri[w] = c0; q_pos[w] = pos; ++w; }
+                if (need & 2u)  { q_tri[w] = c1; q_pos[w] = pos; ++w; }
+                if (need & 4u)  { q_tri[w] = c2; q_pos[w] = pos; ++w; }
+                if (need & 8u)  { q_tri[w] = c3; q_pos[w] = pos; ++w; }
+                if (need & 16u) { q_tri[w] = c4; q_pos[w] = pos; ++w; }
+                if (need & 32u) { q_tri[w] = c5; q_pos[w] = pos; ++w; }
+                if (need & 64u) { q_tri[w] = c6; q_pos[w] = pos; ++w; }
+                return __shfl_sync(0xffffffffu, incl, 31);
+            };
+            // the owner replays the results of its pairs in neighbour order (they lie in that order from `off` on)
+            auto apply = [&](uint32_t need, uint32_t pos, float phi, int ct, int n, int off) {
+                if (!need) return;
+                bool changed = false;
+                for (int w = off; need; need &= need - 1, ++w) {
+                    const float d = __uint_as_float(q_pos[w]);
+                    if (d < phi) { phi = d; ct = (int)q_tri[w]; changed = true; }
                 }
+                if (changed) {
+                    const uint8_t code = (uint8_t)(s + 1);
+                    K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)code << 27) | (uint32_t)ct;
+                    if (!CL) {
+                        // in every direction d this node is upwind of nodes 1..3 levels further on: stamp those
+                        // levels (codes only grow and all writers of a sweep write the same value)
+                        const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
+#pragma unroll
+                        for (int dq = 0; dq < 8; ++dq) {
+                            int ei, ej, ek;
+                            sweep_dir(dq, ei, ej, ek);
+                            const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) +
+                                           (ek > 0 ? pk - 1 : nk - 2 - pk);
+                            uint8_t* row = s_dirty + dq * nlev;
+#pragma unroll
+                            for (int up = 1; up <= 3; ++up) {
+                                const int l = lv + up;
+                                if (l >= 0 && l < nlev) row[l] = code;
+                            }
+                        }
+                    }
+                }
+            };
+            // The nodes of a level are independent: a warp runs the node phase of two of its rounds back to back
+            // (their loads overlap, their pairs share one queue), evaluates the queue densely, then applies.
+            for (int qb = beg + crank * NT + warp * 32; qb < end; qb += R * NT * csize) {
+                uint32_t needA, posA, needB = 0, posB = 0;
+                float phiA, phiB = 0.f;
+                int ctA, nA, offA, ctB = -1, nB = 0, offB = 0;
+                int W = node_phase(qb + lane, 0, needA, posA, phiA, ctA, nA, offA);
+                if (R == 2 && qb + NT * csize < end) W += node_phase(qb + NT * csize + lane, W, needB, posB, phiB, ctB, nB, offB);
+                if (W == 0) continue;
                 __syncwarp();
                 for (int e = lane; e < W; e += 32) {
                     uint32_t pp = q_pos[e];
@@ -839,40 +882,9 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     ++n_eval;
                 }
                 __syncwarp();
-                if (need) {
-                    int r = off;
-                    bool changed = false;
-                    float d;
-                    if (need & 1u)  { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c0; changed = true; } }
-                    if (need & 2u)  { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c1; changed = true; } }
-                    if (need & 4u)  { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c2; changed = true; } }
-                    if (need & 8u)  { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c3; changed = true; } }
-                    if (need & 16u) { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c4; changed = true; } }
-                    if (need & 32u) { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c5; changed = true; } }
-                    if (need & 64u) { d = __uint_as_float(q_pos[r++]); if (d < phi) { phi = d; ct = c6; changed = true; } }
-                    if (changed) {
-                        const uint8_t code = (uint8_t)(s + 1);
-                        K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)code << 27) | (uint32_t)ct;
-                        if (!CL) {
-                            // in every direction d this node is upwind of nodes 1..3 levels further on: stamp those
-                            // levels (codes only grow and all writers of a sweep write the same value)
-                            const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
-#pragma unroll
-                            for (int dq = 0; dq < 8; ++dq) {
-                                int ei, ej, ek;
-                                sweep_dir(dq, ei, ej, ek);
-                                const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) +
-                                               (ek > 0 ? pk - 1 : nk - 2 - pk);
-                                uint8_t* row = s_dirty + dq * nlev;
-#pragma unroll
-                                for (int up = 1; up <= 3; ++up) {
-                                    const int l = lv + up;
-                                    if (l >= 0 && l < nlev) row[l] = code;
-                                }
-                            }
-                        }
-                    }
-                }
+                apply(needA, posA, phiA, ctA, nA, offA);
+                if (R == 2) apply(needB, posB, phiB, ctB, nB, offB);
+                __syncwarp();                       // the queue is free again
             }
             if (CL) cluster_barrier(); else __syncthreads();
         }
@@ -983,7 +995,7 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
                     u64* cnt, cudaStream_t stream)
 {
     const int lev_words = (nlev + 1 + 3) & ~3;
-    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * kSweepQueue) * 4 + (size_t)8 * nlev;
+    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue) * 4 + (size_t)8 * nlev;
     auto kern = tdf_sweep_kernel<NT, CL>;
     G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
