@@ -371,16 +371,20 @@ def test_host_abi_chunked_path_equals_device_abi(g3d, count, n):
     L.g3d_context_destroy(ctx)
 
 
-@pytest.mark.parametrize("tiled", [None, "1"])
-def test_randomised_parity_campaign(g3d, tiled):
+@pytest.mark.parametrize("tiled,sweep_threads", [(None, None), ("1", None), ("1", "128"), ("0", "256")])
+def test_randomised_parity_campaign(g3d, tiled, sweep_threads):
     """A short run of tools/fuzz_parity.py (random soups, degenerate / huge triangles, random grids and poses), once
-    with the kernel choice left to the library (single meshes: scatter band init) and once with the tiled band init
-    forced for every case."""
+    with the kernel choice left to the library (single meshes: scatter band init, 1,024-thread sweeps) and then with
+    the batch-sized kernels forced onto every case: tiled band init, 128- and 256-thread sweep CTAs (two rounds of a
+    level per evaluation queue)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
     env.pop("G3D_INIT_TILED", None)
+    env.pop("G3D_SWEEP_THREADS", None)
     if tiled:
         env["G3D_INIT_TILED"] = tiled
+    if sweep_threads:
+        env["G3D_SWEEP_THREADS"] = sweep_threads
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--meshes", "32",
                           "--poses", "100" if tiled is None else "0", "--seed", "5"],
                          capture_output=True, text=True, timeout=900, env=env)
