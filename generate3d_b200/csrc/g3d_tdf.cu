@@ -804,14 +804,6 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                         need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
                         need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
                         need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
-                        // start pulling the triangle records now; they are consumed after the queue is built
-                        if (need & 1u) prefetch_l1(T + 4 * (int64_t)c0);
-                        if (need & 2u) prefetch_l1(T + 4 * (int64_t)c1);
-                        if (need & 4u) prefetch_l1(T + 4 * (int64_t)c2);
-                        if (need & 8u) prefetch_l1(T + 4 * (int64_t)c3);
-                        if (need & 16u) prefetch_l1(T + 4 * (int64_t)c4);
-                        if (need & 32u) prefetch_l1(T + 4 * (int64_t)c5);
-                        if (need & 64u) prefetch_l1(T + 4 * (int64_t)c6);
                     }
                 }
                 if (!__any_sync(0xffffffffu, need != 0)) return 0;
