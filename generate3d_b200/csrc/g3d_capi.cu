@@ -95,30 +95,36 @@ constexpr int kHostChunks = 4;
 
 struct g3d_context {
     int device = 0;
-    cudaStream_t stream = nullptr;                  // kernels and device->host copies
+    cudaStream_t stream = nullptr;                  // kernels
     cudaStream_t s_in = nullptr;                    // host->device copies of the host-buffer front end
-    cudaEvent_t ev_in[kHostChunks] = {};
-    char* arena = nullptr;
-    size_t arena_bytes = 0;
+    cudaStream_t s_out = nullptr;                   // device->host copies: a queue of their own, so that batch k's results
+                                                    // leave while batch k+1's inputs arrive (pipelined submit / wait)
+    // two batches can be in flight: slot b has its own arena and events
+    cudaEvent_t ev_in[2][kHostChunks] = {};         // chunk landed on the device
+    cudaEvent_t ev_fin[2][kHostChunks] = {};        // chunk finalised, results may leave
+    cudaEvent_t ev_done[2] = {};                    // all results of the slot's batch are on the host
+    bool busy[2] = { false, false };
+    char* arena[2] = { nullptr, nullptr };
+    size_t arena_bytes[2] = { 0, 0 };
 };
 
 namespace {
 
-// grow-only device arena; returns nullptr on failure (error already set)
-char* arena_reserve(g3d_context* c, size_t bytes)
+// grow-only device arena per slot; returns nullptr on failure (error already set)
+char* arena_reserve(g3d_context* c, size_t bytes, int slot = 0)
 {
-    if (bytes <= c->arena_bytes) return c->arena;
-    if (c->arena) {
-        cudaStreamSynchronize(c->stream);
-        cudaFree(c->arena);
-        c->arena = nullptr;
-        c->arena_bytes = 0;
+    if (bytes <= c->arena_bytes[slot]) return c->arena[slot];
+    if (c->arena[slot]) {
+        cudaDeviceSynchronize();                    // the other slot may be in flight; cudaFree synchronises anyway
+        cudaFree(c->arena[slot]);
+        c->arena[slot] = nullptr;
+        c->arena_bytes[slot] = 0;
     }
     size_t want = align_up(bytes + bytes / 8, (size_t)1 << 20);
-    cudaError_t e = cudaMalloc((void**)&c->arena, want);
+    cudaError_t e = cudaMalloc((void**)&c->arena[slot], want);
     if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc(arena)"); return nullptr; }
-    c->arena_bytes = want;
-    return c->arena;
+    c->arena_bytes[slot] = want;
+    return c->arena[slot];
 }
 
 struct Carver {
@@ -269,7 +275,14 @@ int g3d_context_create(int32_t device, g3d_context** ctx)
     c->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
-    for (int i = 0; i < kHostChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    for (int b = 0; b < 2; ++b) {
+        for (int i = 0; i < kHostChunks && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&c->ev_in[b][i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fin[b][i], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { g3d_context_destroy(c); return cuda_fail(e, "cudaStreamCreate/cudaEventCreate"); }
     *ctx = c;
     return G3D_OK;
@@ -281,26 +294,41 @@ void g3d_context_destroy(g3d_context* c)
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
-    for (int i = 0; i < kHostChunks; ++i) if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
-    if (c->arena) cudaFree(c->arena);
+    if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }
+    for (int b = 0; b < 2; ++b) {
+        for (int i = 0; i < kHostChunks; ++i) {
+            if (c->ev_in[b][i]) cudaEventDestroy(c->ev_in[b][i]);
+            if (c->ev_fin[b][i]) cudaEventDestroy(c->ev_fin[b][i]);
+        }
+        if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]);
+        if (c->arena[b]) cudaFree(c->arena[b]);
+    }
     delete c;
 }
 
-size_t g3d_context_arena_bytes(const g3d_context* c) { return c ? c->arena_bytes : 0; }
+size_t g3d_context_arena_bytes(const g3d_context* c) { return c ? c->arena_bytes[0] + c->arena_bytes[1] : 0; }
 
-int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_off, const uint32_t* tris,
-                       const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
-                       const g3d_tdf_outputs* out)
+int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t* vert_off, const uint32_t* tris,
+                              const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
+                              const g3d_tdf_outputs* out, int32_t* ticket)
 {
-    if (!c || !params || !out) { set_error("tdf_host: NULL argument"); return G3D_ERR_INVALID; }
+    if (!c || !params || !out || !ticket) { set_error("tdf_host: NULL argument"); return G3D_ERR_INVALID; }
+    *ticket = -1;
     if (n_mesh < 0) { set_error("tdf_host: n_mesh < 0"); return G3D_ERR_INVALID; }
-    if (n_mesh == 0) return G3D_OK;
-    if (!vert_off || !tri_off) { set_error("tdf_host: offsets are NULL"); return G3D_ERR_INVALID; }
-    const int64_t nv = vert_off[n_mesh], nt = tri_off[n_mesh];
+    if (n_mesh > 0 && (!vert_off || !tri_off)) { set_error("tdf_host: offsets are NULL"); return G3D_ERR_INVALID; }
+    const int64_t nv = n_mesh ? vert_off[n_mesh] : 0, nt = n_mesh ? tri_off[n_mesh] : 0;
     if (nv < 0 || nt < 0 || (nv > 0 && !verts) || (nt > 0 && !tris)) { set_error("tdf_host: bad mesh arrays"); return G3D_ERR_INVALID; }
     for (int m = 0; m < n_mesh; ++m)
         if (vert_off[m + 1] < vert_off[m] || tri_off[m + 1] < tri_off[m]) { set_error("tdf_host: offsets not monotone"); return G3D_ERR_INVALID; }
+    const int slot = !c->busy[0] ? 0 : (!c->busy[1] ? 1 : -1);
+    if (slot < 0) { set_error("tdf_host: two batches are already in flight; wait for one first"); return G3D_ERR_INVALID; }
     G3D_CUDA_TRY(cudaSetDevice(c->device));
+    if (n_mesh == 0) {                              // nothing to do; the ticket is still valid
+        G3D_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_out));
+        c->busy[slot] = true;
+        *ticket = slot;
+        return G3D_OK;
+    }
     const int64_t nvox = (int64_t)params->ni * params->nj * params->nk, pw = (nvox + 31) / 32;
     const size_t ws_bytes = g3d_tdf_workspace_bytes(n_mesh, nv, nt, params);
 
@@ -323,55 +351,82 @@ int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_o
     g3d_tdf_outputs d{};
     float* dv; int64_t* dvo; uint32_t* dt; int64_t* dto; void* ws;
     size_t need = layout(nullptr, d, dv, dvo, dt, dto, ws);
-    char* base = arena_reserve(c, need);
+    char* base = arena_reserve(c, need, slot);
     if (!base) return G3D_ERR_CUDA;
     layout(base, d, dv, dvo, dt, dto, ws);
 
-    // The meshes cross PCIe in up to 4 chunks on a copy stream; the per-triangle stage of a chunk (records,
-    // boxes, parity, band init) starts as soon as that chunk has landed, so most of the host->device time
-    // hides behind kernels. The whole-batch stage (sweeps) then runs once, on the full batch.
+    // The meshes cross PCIe in up to 4 chunks on the input stream; the per-triangle stage of a chunk (records,
+    // boxes, parity, band init) starts as soon as that chunk has landed, so most of the host->device time hides
+    // behind kernels. The sweeps then run once on the full batch; the epilogue runs per chunk and each chunk's
+    // results start their way back on the output stream while the next chunk is still being finalised. With a
+    // second batch submitted before the first is waited for, its inputs arrive during the first one's sweeps and
+    // the first one's results leave during its staging: the kernel stream never waits for PCIe.
     cudaStream_t s = c->stream;
+    cudaEvent_t* ev_in = c->ev_in[slot];
+    cudaEvent_t* ev_fin = c->ev_fin[slot];
+    auto bail = [&](int code) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(c->s_out); return code; };
     const int nch = n_mesh >= 64 ? kHostChunks : 1;
-    G3D_CUDA_TRY(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, s));
-    G3D_CUDA_TRY(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, s));
-    int rc = tdf_begin(nv, nt, n_mesh, *params, d, ws, ws_bytes, s);
-    if (rc != G3D_OK) return rc;
+    auto chunk_lo = [&](int ch) { return (int)((int64_t)n_mesh * ch / nch); };
+    G3D_CUDA_TRY(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
+    G3D_CUDA_TRY(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
     for (int ch = 0; ch < nch; ++ch) {
-        const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch);
+        const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1);
         const int64_t v0 = vert_off[m0], v1 = vert_off[m1], t0 = tri_off[m0], t1 = tri_off[m1];
         if (v1 > v0) G3D_CUDA_TRY(cudaMemcpyAsync(dv + 3 * v0, verts + 3 * v0, (size_t)(v1 - v0) * 12, cudaMemcpyHostToDevice, c->s_in));
         if (t1 > t0) G3D_CUDA_TRY(cudaMemcpyAsync(dt + 3 * t0, tris + 3 * t0, (size_t)(t1 - t0) * 12, cudaMemcpyHostToDevice, c->s_in));
-        G3D_CUDA_TRY(cudaEventRecord(c->ev_in[ch], c->s_in));
+        G3D_CUDA_TRY(cudaEventRecord(ev_in[ch], c->s_in));
     }
+    G3D_CUDA_TRY(cudaStreamWaitEvent(s, ev_in[0], 0));           // the offset arrays precede chunk 0 on the input stream
+    int rc = tdf_begin(nv, nt, n_mesh, *params, d, ws, ws_bytes, s);
+    if (rc != G3D_OK) return bail(rc);
     for (int ch = 0; ch < nch; ++ch) {
-        const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch);
-        G3D_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_in[ch], 0));
+        const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1);
+        G3D_CUDA_TRY(cudaStreamWaitEvent(s, ev_in[ch], 0));
         rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], m0, m1, nt, n_mesh, *params, d, ws, s);
-        if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
+        if (rc != G3D_OK) return bail(rc);
     }
     rc = tdf_solve(dto, nt, n_mesh, *params, ws, s);
-    if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
-    // The epilogue runs per chunk of meshes and each chunk's results start their way back (on the copy stream,
-    // idle by now) while the next chunk is still being finalised.
+    if (rc != G3D_OK) return bail(rc);
     const size_t gv = (size_t)nvox;
     for (int ch = 0; ch < nch; ++ch) {
-        const int m0 = (int)((int64_t)n_mesh * ch / nch), m1 = (int)((int64_t)n_mesh * (ch + 1) / nch), nm = m1 - m0;
+        const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1), nm = m1 - m0;
         rc = tdf_finalize(dvo, dto, nt, n_mesh, m0, m1, *params, d, ws, s);
-        if (rc != G3D_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); return rc; }
-        G3D_CUDA_TRY(cudaEventRecord(c->ev_in[ch], s));
-        G3D_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_in[ch], 0));
+        if (rc != G3D_OK) return bail(rc);
+        G3D_CUDA_TRY(cudaEventRecord(ev_fin[ch], s));
+        G3D_CUDA_TRY(cudaStreamWaitEvent(c->s_out, ev_fin[ch], 0));
         const size_t gb = (size_t)nm * gv * 4, go = (size_t)m0 * gv;
-        if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf + go, d.sdf + go, gb, cudaMemcpyDeviceToHost, c->s_in));
-        if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf + go, d.tdf + go, gb, cudaMemcpyDeviceToHost, c->s_in));
-        if (out->tdflog) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdflog + go, d.tdflog + go, gb, cudaMemcpyDeviceToHost, c->s_in));
-        if (out->occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_bits + (size_t)m0 * pw, d.occ_bits + (size_t)m0 * pw, (size_t)nm * pw * 4, cudaMemcpyDeviceToHost, c->s_in));
-        if (out->occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_f32 + go, d.occ_f32 + go, gb, cudaMemcpyDeviceToHost, c->s_in));
-        if (out->closest_tri) G3D_CUDA_TRY(cudaMemcpyAsync(out->closest_tri + go, d.closest_tri + go, gb, cudaMemcpyDeviceToHost, c->s_in));
+        if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf + go, d.sdf + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf + go, d.tdf + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->tdflog) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdflog + go, d.tdflog + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_bits + (size_t)m0 * pw, d.occ_bits + (size_t)m0 * pw, (size_t)nm * pw * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_f32 + go, d.occ_f32 + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->closest_tri) G3D_CUDA_TRY(cudaMemcpyAsync(out->closest_tri + go, d.closest_tri + go, gb, cudaMemcpyDeviceToHost, c->s_out));
     }
-    if (out->status) G3D_CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, s));
-    G3D_CUDA_TRY(cudaStreamSynchronize(c->s_in));
-    G3D_CUDA_TRY(cudaStreamSynchronize(s));
+    if (out->status) G3D_CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, c->s_out));
+    G3D_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_out));
+    c->busy[slot] = true;
+    *ticket = slot;
     return G3D_OK;
+}
+
+int g3d_tdf_batch_host_wait(g3d_context* c, int32_t ticket)
+{
+    if (!c || ticket < 0 || ticket > 1 || !c->busy[ticket]) { set_error("tdf_host_wait: no such batch in flight"); return G3D_ERR_INVALID; }
+    G3D_CUDA_TRY(cudaSetDevice(c->device));
+    c->busy[ticket] = false;
+    G3D_CUDA_TRY(cudaEventSynchronize(c->ev_done[ticket]));
+    G3D_CUDA_TRY(cudaGetLastError());
+    return G3D_OK;
+}
+
+int g3d_tdf_batch_host(g3d_context* c, const float* verts, const int64_t* vert_off, const uint32_t* tris,
+                       const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
+                       const g3d_tdf_outputs* out)
+{
+    int32_t ticket = -1;
+    int rc = g3d_tdf_batch_host_submit(c, verts, vert_off, tris, tri_off, n_mesh, params, out, &ticket);
+    if (rc != G3D_OK) return rc;
+    return g3d_tdf_batch_host_wait(c, ticket);
 }
 
 int g3d_raycast_batch_host(g3d_context* c, const uint8_t* depth, const float* pose, int32_t n_view, int32_t H,
@@ -382,6 +437,7 @@ int g3d_raycast_batch_host(g3d_context* c, const uint8_t* depth, const float* po
     if (n_view < 0 || H < 1 || W < 1 || dim < 1) { set_error("raycast_host: bad sizes"); return G3D_ERR_INVALID; }
     if (n_view == 0) return G3D_OK;
     if (!depth || !pose) { set_error("raycast_host: null input"); return G3D_ERR_INVALID; }
+    if (c->busy[0] || c->busy[1]) { set_error("raycast_host: a submitted TDF batch is still in flight on this context; wait for it first"); return G3D_ERR_INVALID; }
     G3D_CUDA_TRY(cudaSetDevice(c->device));
     const int64_t nvox = (int64_t)dim * dim * dim, pw = (nvox + 31) / 32;
     const size_t img = (size_t)n_view * H * W;

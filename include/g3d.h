@@ -135,8 +135,8 @@ int g3d_raycast_batch(const uint8_t* depth, const float* pose, int32_t n_view, i
                       uint32_t* occ_bits, float* occ_f32, int64_t* index_map, void* cuda_stream);
 
 /* ------------------------------------------------- host-buffer front end ----
- * What a cgo/ctypes/CLI caller with host arrays uses. The context owns a
- * grow-only device arena and one stream on `device`. */
+ * What a cgo/ctypes/CLI caller with host arrays uses. The context owns grow-only
+ * device arenas and its own streams (kernels, copies in, copies out) on `device`. */
 typedef struct g3d_context g3d_context;
 
 int  g3d_context_create(int32_t device, g3d_context** ctx);
@@ -148,6 +148,17 @@ size_t g3d_context_arena_bytes(const g3d_context* ctx);
 int g3d_tdf_batch_host(g3d_context* ctx, const float* verts, const int64_t* vert_off,
                        const uint32_t* tris, const int64_t* tri_off, int32_t n_mesh,
                        const g3d_tdf_params* params, const g3d_tdf_outputs* out);
+
+/* The same call split in two, so that a loop over batches keeps the GPU busy: submit batch k+1, then wait for
+ * batch k. Up to two batches are in flight per context (each in its own device arena); the inputs of the later one
+ * cross PCIe while the earlier one is being swept, and the earlier one's results leave while the later one is
+ * staged. `*ticket` identifies the batch for the wait. All host arrays of a submitted batch (inputs, offsets,
+ * outputs) must stay valid and untouched until its wait returns; pinned memory makes the copies asynchronous,
+ * pageable memory works but serialises. g3d_tdf_batch_host is submit followed by wait. */
+int g3d_tdf_batch_host_submit(g3d_context* ctx, const float* verts, const int64_t* vert_off,
+                              const uint32_t* tris, const int64_t* tri_off, int32_t n_mesh,
+                              const g3d_tdf_params* params, const g3d_tdf_outputs* out, int32_t* ticket);
+int g3d_tdf_batch_host_wait(g3d_context* ctx, int32_t ticket);
 
 /* Host twin of g3d_raycast_batch. */
 int g3d_raycast_batch_host(g3d_context* ctx, const uint8_t* depth, const float* pose,

@@ -435,3 +435,54 @@ def test_band_init_kernels_match_oracle_on_ragged_multiblock_batch(g3d, oracle, 
         want = oracle.make_level_set3(Ts[m], Vs[m], origin, dx, ni, nj, nk)
         assert np.array_equal(_bits(sdf[m]), _bits(want["phi"])), m
         assert np.array_equal(ct[m], want["closest_tri"]), m
+
+
+def test_host_abi_submit_wait_pipeline(g3d):
+    """g3d_tdf_batch_host_submit / _wait: two batches in flight on one context give the results of the synchronous
+    call, tickets are checked, a third submit is refused, raycast_host is refused while a batch is in flight."""
+    from generate3d_b200 import dfgen
+    L = g3d.lib()
+    ctx = C.c_void_p()
+    g3d.check(L.g3d_context_create(0, C.byref(ctx)))
+    p = g3d.TdfParams()
+    g2w = np.zeros(16, np.float32)
+    g3d.check(L.g3d_dfgen_geometry(32, 0, 1, None, None, C.byref(p), g2w.ctypes.data))
+    p.trunc, p.occ_thresh, p.mode = 3.0, 1.0, 0
+    batches = []
+    for b, (count, n, seed) in enumerate(((80, 3, 900), (70, 2, 901), (96, 2, 902))):
+        V, voff, T, toff = S.table_batch(count, n, first_seed=seed)
+        hV, hT = torch.from_numpy(V).pin_memory(), torch.from_numpy(T.view(np.int32)).pin_memory()
+        sdf = torch.empty((count, 32, 32, 32), dtype=torch.float32).pin_memory()
+        st = torch.empty((count,), dtype=torch.int32).pin_memory()
+        o = g3d.TdfOutputs()
+        o.sdf, o.status = sdf.data_ptr(), st.data_ptr()
+        batches.append((V, voff, T, toff, hV, hT, sdf, st, o, count))
+
+    def submit(bt):
+        tk = C.c_int32(-1)
+        rc = L.g3d_tdf_batch_host_submit(ctx, bt[4].data_ptr(), bt[1].ctypes.data, bt[5].data_ptr(), bt[3].ctypes.data,
+                                         bt[9], C.byref(p), C.byref(bt[8]), C.byref(tk))
+        return rc, tk.value
+    rc0, t0 = submit(batches[0])
+    rc1, t1 = submit(batches[1])
+    assert rc0 == 0 and rc1 == 0 and {t0, t1} == {0, 1}
+    rc2, t2 = submit(batches[2])
+    assert rc2 == -1 and t2 == -1 and b"in flight" in L.g3d_last_error()      # two is the limit
+    d = torch.zeros((1, 64, 64), dtype=torch.uint8)
+    assert L.g3d_raycast_batch_host(ctx, d.data_ptr(), g2w.ctypes.data, 1, 64, 64, 65.0, 32.0, 32.0, 511, 32, None, None, None) == -1
+    g3d.check(L.g3d_tdf_batch_host_wait(ctx, t0))
+    assert L.g3d_tdf_batch_host_wait(ctx, t0) == -1                           # already collected
+    rc2, t2 = submit(batches[2])                                              # the freed slot is reused while t1 is in flight
+    assert rc2 == 0 and t2 == t0
+    g3d.check(L.g3d_tdf_batch_host_wait(ctx, t1))
+    g3d.check(L.g3d_tdf_batch_host_wait(ctx, t2))
+    assert L.g3d_tdf_batch_host_wait(ctx, 5) == -1
+    for bt in batches:
+        want = dfgen.tdf_batch(bt[0], bt[1], bt[2], bt[3], outputs=("sdf",))["sdf"].cpu().numpy()
+        assert not bt[7].numpy().any()
+        assert np.array_equal(_bits(bt[6].numpy()), _bits(want))
+    # an empty batch is a valid ticket too
+    tk = C.c_int32(-1)
+    g3d.check(L.g3d_tdf_batch_host_submit(ctx, None, None, None, None, 0, C.byref(p), C.byref(batches[0][8]), C.byref(tk)))
+    g3d.check(L.g3d_tdf_batch_host_wait(ctx, tk.value))
+    L.g3d_context_destroy(ctx)
