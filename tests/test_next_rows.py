@@ -151,3 +151,15 @@ def test_zbuffer_index_map_gpu_vs_reference(g3d, oracle, golden_dir):
     assert tuple(g.shape) == (32 ** 3,)
     L = g3d.lib()
     assert L.g3d_zbuffer_index_map(None, None, 1, 1, 512, 512, 525.0, 256.0, 256.0, 511, 32, None, None) == -1
+
+
+def test_pack_occupancy_mask_bit_order():
+    """Host-side packing used by the ProjectionHelper mirror: bit lin & 31 of word lin >> 5, ragged tail padded."""
+    from generate3d_b200.perspective_projection import pack_occupancy_mask
+    rng = np.random.default_rng(1)
+    for n in (32, 64, 100, 32768):
+        m = rng.uniform(size=(3, n)) < 0.3
+        got = pack_occupancy_mask(torch.from_numpy(m)).numpy().view(np.uint32)
+        pad = (-n) % 32
+        want = np.packbits(np.pad(m, ((0, 0), (0, pad))).reshape(3, -1, 32), axis=-1, bitorder="little").view(np.uint32).reshape(3, -1)
+        assert got.shape == want.shape and np.array_equal(got, want), n
