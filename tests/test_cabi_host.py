@@ -36,6 +36,13 @@ def test_no_gpu_means_error_not_fallback(g3d):
     ctx = C.c_void_p()
     assert g3d.lib().g3d_context_create(0, C.byref(ctx)) != 0
     assert g3d.lib().g3d_last_error()
+    # the projection-layer mirror and the split host call have no CPU path either
+    from generate3d_b200 import perspective_projection as pp
+    with pytest.raises(RuntimeError):
+        pp.ProjectionHelper()
+    tk = C.c_int32(7)
+    assert g3d.lib().g3d_tdf_batch_host_submit(None, None, None, None, None, 0, None, None, C.byref(tk)) == -1
+    assert g3d.lib().g3d_tdf_batch_host_wait(None, 0) == -1
 
 
 @pytest.mark.parametrize("dim,pad,unit", [(32, 0, 1), (64, 0, 1), (128, 0, 1), (32, 1, 1), (32, 2, 1), (20, 0, 1)])
