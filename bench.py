@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0] / [3] / [4] legs")
+    ap.add_argument("--dataset-models", type=int, default=100000, help="configs[4]: models in the whole data set (sharded over the ranks)")
     return ap.parse_args()
 
 
@@ -116,7 +118,7 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------- CPU arms
 
-def cpu_tdf_reference(V, voff, T, toff, meshes, threads):
+def cpu_tdf_reference(V, voff, T, toff, meshes, threads, keep=None):
     """Time the reference make_level_set3 (or the C port) on `meshes` models with `threads` host threads.
     Returns (seconds, kind)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -131,6 +133,8 @@ def cpu_tdf_reference(V, voff, T, toff, meshes, threads):
             phi = O.ref_make_level_set3(t, v, g["origin"], g["dx"], DIM, DIM, DIM)       # as shipped: asserts on
         else:
             phi = O.make_level_set3(t, v, g["origin"], g["dx"], DIM, DIM, DIM)["phi"]
+        if keep is not None:
+            keep[m] = phi
         return float(phi[0, 0, 0])
 
     t0 = time.perf_counter()
@@ -141,6 +145,15 @@ def cpu_tdf_reference(V, voff, T, toff, meshes, threads):
         with ThreadPoolExecutor(threads) as ex:
             list(ex.map(one, meshes))
     return time.perf_counter() - t0, kind
+
+
+def cpu_tdf_single(v, t, dim):
+    """The reference's make_level_set3 on one mesh at dim^3 (unit cube): (phi, kind)."""
+    from oracle import oracle as O
+    g = O.dfgen_geometry(dim)
+    if O.ref_available(ndebug=False):
+        return O.ref_make_level_set3(t, v, g["origin"], g["dx"], dim, dim, dim), "reference"
+    return O.make_level_set3(t, v, g["origin"], g["dx"], dim, dim, dim)["phi"], "port"
 
 
 def cpu_raycast_port(depth, poses, focal):
@@ -187,6 +200,99 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------- B200 arm
+
+def bench_other_configs(args, rank, world, dev, barrier, peak_tf, nominal_tf):
+    """BASELINE.json configs[0], [3] and [4] (configs[1] is the raycast leg, configs[2] the headline): each timed with
+    CUDA events after warm-up, evaluation counts from an instrumented untimed run. Returns (dict, kernel launches)."""
+    import torch
+    from generate3d_b200 import _lib, dataset_gen, dfgen, shard, synthetic as S
+    L = _lib.lib()
+    ev = (C.c_uint64 * 4)()
+    sm = (C.c_float * 8)()
+    names = ["fill", "prep", "band_init", "order", "sweep", "finalize", "exact", "raycast"]
+    launches = 0
+    res = {}
+
+    def one_mesh_case(n, dim, steps, warm):
+        nonlocal launches
+        v, t = S.table_mesh(n, seed=rank)
+        dv, dt = torch.from_numpy(v).to(dev), torch.from_numpy(t.view(np.int32)).to(dev)
+        dvo, dto = torch.tensor([0, len(v)], device=dev), torch.tensor([0, len(t)], device=dev)
+        outs = ("sdf", "tdf", "tdflog", "occ_bits", "status")
+        case = {"tris": int(len(t)), "dim": dim, "outputs": list(outs)}
+        keep = {}
+        for mode in ("faithful", "exact"):
+            def step(o):
+                return dfgen.tdf_batch(dv, dvo, dt, dto, dim=dim, trunc=TRUNC, mode=mode, outputs=outs, out=o)
+            _lib.check(L.g3d_profile_enable(2))
+            o = step(None)
+            torch.cuda.synchronize()
+            _lib.check(L.g3d_profile_read(None, ev))
+            evals = {"init": int(ev[0]), "sweep": int(ev[1]), "exact_pairs": int(ev[2]), "exact_box_tests": int(ev[3])}
+            _lib.check(L.g3d_profile_enable(1))
+            for _ in range(warm):
+                step(o)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stage = np.zeros(8)
+            a.record()
+            for _ in range(steps):
+                step(o)
+                _lib.check(L.g3d_profile_read(sm, None))
+                stage += np.frombuffer(sm, np.float32)
+            b.record()
+            barrier()
+            ms = shard.all_reduce_max(a.elapsed_time(b) / steps, dev)
+            stage /= steps
+            st = {k: round(float(x), 4) for k, x in zip(names, stage) if x > 0}
+            dom = max(("band_init", "sweep", "exact"), key=lambda k: st.get(k, 0.0))
+            dom_evals = {"band_init": evals["init"], "sweep": evals["sweep"], "exact": evals["exact_pairs"]}[dom]
+            ach = FLOP_PER_EVAL * dom_evals / (st[dom] * 1e-3) / 1e12 if st.get(dom) else 0.0
+            case[mode] = {"ms_per_mesh": ms, "value": world * dim ** 3 / (ms * 1e-3), "unit": "voxels/s", "steps": steps,
+                          "stages_ms": st, "evals_per_mesh": evals,
+                          "roofline": {"kernel": "tdf_%s_kernel" % dom, "bound": "fp32", "achieved": ach, "peak": peak_tf,
+                                       "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                                       "frac_of_nominal": ach / nominal_tf, "evals_per_launch": dom_evals,
+                                       "kernel_ms": st.get(dom), "traffic": None}}
+            launches += (6 if mode == "faithful" else 4) * (steps + warm + 1)
+            keep[mode] = o["sdf"][0].clone()
+            assert int(o["status"].sum().item()) == 0
+        return case, (v, t, keep)
+
+    c0, k0 = one_mesh_case(9, 32, max(args.steps, 10), 3)
+    c0["workload"] = "configs[0]: dfgen TDF + tdflog of one synthetic 4,860-triangle table mesh at 32^3, truncation 3 (a latency case: the 300 KB mesh is L2-resident by nature)"
+    res["configs[0]"] = c0
+    c3, k3 = one_mesh_case(58, 128, max(2, min(args.steps, 5)), 2)
+    c3["workload"] = "configs[3]: 128^3 TDF of one 201,840-triangle table mesh (compute-bound stress); inputs + keys 46 MB"
+    res["configs[3]"] = c3
+
+    # configs[4]: the whole data set sharded over the ranks (strong scaling), inputs generated on the device per chunk
+    total = args.dataset_models
+    lo, hi = dataset_gen.shard_models(total, rank, world)
+    dataset_gen.voxelize_shard(lo, min(hi - lo, 64), chunk=64, device=dev)           # warm-up: templates, workspace
+    tm = {}
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    shard_out = dataset_gen.voxelize_shard(lo, hi - lo, chunk=args.meshes, device=dev, keep=("tdf", "occ_bits"), timing=tm)
+    b.record()
+    barrier()
+    bad = int(shard.all_reduce_sum(int((shard_out["status"] != 0).sum().item()), dev))
+    ms_all = shard.all_reduce_max(a.elapsed_time(b), dev)
+    ms_tdf = shard.all_reduce_max(tm["tdf_ms"], dev)
+    res["configs[4]"] = {
+        "workload": "configs[4]: %d-model synthetic data set (19,440-tri tables -> 32^3 tdf + packed occupancy, faithful mode), "
+                    "models sharded contiguously over %d GPU(s), inputs generated on the device per %d-model chunk, results "
+                    "resident in HBM" % (total, world, args.meshes),
+        "scaling": "strong", "models": total, "models_per_rank": hi - lo, "chunks_per_rank": tm["chunks"],
+        "value": total * DIM ** 3 / (ms_tdf * 1e-3), "unit": "voxels/s", "tdf_ms": ms_tdf,
+        "value_incl_generation": total * DIM ** 3 / (ms_all * 1e-3), "total_ms": ms_all,
+        "resident_output_gb": sum(v.numel() * v.element_size() for v in shard_out.values()) / 1e9,
+        "models_with_error_flags": bad}
+    launches += 6 * (tm["chunks"] + 1)
+    del shard_out
+    return res, launches, (k0, k3)
+
 
 def run_b200(args, rank, world, local):
     import torch
@@ -317,6 +423,12 @@ def run_b200(args, rank, world, local):
                                    "evals_per_launch": onev, "kernel_ms": okms}}
         tdf_launches += (4 if other == "exact" else 6) * (nst + 2)
         del oo
+
+    # ---- the other BASELINE configs: [0] one 5k-tri mesh, [3] 128^3 x 200k tris, [4] the 100k-model data set
+    configs, keep0, keep3 = None, None, None
+    if not args.no_configs:
+        configs, cl, (keep0, keep3) = bench_other_configs(args, rank, world, dev, barrier, float(tf.value), nominal)
+        tdf_launches += cl
 
     # ---- raycast: configs[1] (20 views 256^2, one launch) and a batched leg (> L2) for the HBM roofline
     d20, p20 = S.depth_views(20, 256, 256)
@@ -477,9 +589,27 @@ def run_b200(args, rank, world, local):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = args.cpu_sample or 40
         ns = min(ns, M)
-        secs, kind = cpu_tdf_reference(V, voff, T, toff, list(range(ns)), 1)
+        check = {}
+        secs, kind = cpu_tdf_reference(V, voff, T, toff, list(range(ns)), 1, keep=check)
         cpu = {"value": ns * DIM ** 3 / secs, "unit": "voxels/s", "cores": 1, "kind": kind,
                "sample": "first %d of the %d meshes of the step, single thread (the reference is single-threaded), %.1f s" % (ns, M, secs)}
+        # the checker's results on those meshes against what the timed kernels left in `out` (sdf = phi * dim)
+        gpu_sdf = out["sdf"][:ns].cpu().numpy()
+        n_eq = sum(int(np.array_equal((check[m] * np.float32(DIM)).view(np.uint32), gpu_sdf[m].view(np.uint32))) for m in range(ns))
+        cpu["parity_check"] = {"meshes": ns, "bit_equal_to_gpu": n_eq, "mode": args.mode,
+                               "note": "faithful mode must give %d of %d; exact mode differs beyond |d| = 1 by design" % (ns, ns)}
+        if args.mode == "faithful":
+            assert n_eq == ns, "GPU sdf differs from the CPU reference on the bench batch"
+        if configs is not None:
+            for key, (cv, ct, ckeep), cdim in (("configs[0]", keep0, 32), ("configs[3]", keep3, 128)):
+                t0 = time.perf_counter()
+                phi, ckind = cpu_tdf_single(cv, ct, cdim)
+                dtc = time.perf_counter() - t0
+                eq = bool(np.array_equal((phi * np.float32(cdim)).view(np.uint32), ckeep["faithful"].cpu().numpy().view(np.uint32)))
+                configs[key]["cpu_baseline"] = {"value": cdim ** 3 / dtc, "unit": "voxels/s", "cores": 1, "kind": ckind,
+                                                "sample": "the same mesh, one run, single thread, %.2f s" % dtc,
+                                                "faithful_bit_equal_to_gpu": eq}
+                assert eq, key + ": GPU faithful sdf differs from the CPU reference"
         rs = cpu_raycast_port(d20[:4], p20[:4], 262.5)
         raycast["cpu_baseline"] = {"value": 4 * 65536 / rs, "unit": "rays/s", "cores": 1, "kind": "port",
                                    "sample": "4 of the 20 views, numpy restatement of raycast_depth (the reference's Python loop "
@@ -495,7 +625,7 @@ def run_b200(args, rank, world, local):
                        "trunc": TRUNC, "mode": args.mode, "outputs": list(outputs),
                        "l2": "inputs %.0f MB + outputs %.0f MB per step, larger than the 126 MB L2 (no explicit flush)" % (input_mb, M * DIM ** 3 * 12.125 / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": tdf_launches + ray_launches, "roofline": roofline,
-            "cpu_baseline": cpu, "stages_ms": stages_ms, "evals_per_step": evals, "other_mode": other_mode, "raycast": raycast, "next_rows": next_rows,
+            "cpu_baseline": cpu, "configs": configs, "stages_ms": stages_ms, "evals_per_step": evals, "other_mode": other_mode, "raycast": raycast, "next_rows": next_rows,
             "pair_rate_nominal_per_s": world * M * DIM ** 3 * 60 * args.n ** 2 / (ms_step * 1e-3),
         }
         print(json.dumps(line), flush=True)

@@ -1013,9 +1013,12 @@ int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, c
     // Threads per mesh. Small CTAs win for 32^3-class grids (measured on B200, 1,024 meshes: 128 thr 22.2 ms,
     // 256 thr 24.4, 512 thr 28.4, 1024 thr 31.1): more meshes are resident per SM, so one mesh's barrier
     // wait is covered by another mesh's arithmetic. Large grids get more threads per mesh.
-    static int forced = -1, forced_cl = -1;
-    if (forced < 0) { const char* e = getenv("G3D_SWEEP_THREADS"); forced = e ? atoi(e) : 0; }
-    if (forced_cl < 0) { const char* e = getenv("G3D_SWEEP_CLUSTER"); forced_cl = e ? atoi(e) : 0; }
+    // test / tuning overrides, read per call (the tests flip them between calls)
+    const char* e_nt = getenv("G3D_SWEEP_THREADS");
+    const char* e_cl = getenv("G3D_SWEEP_CLUSTER");
+    int forced = e_nt ? atoi(e_nt) : 0, forced_cl = e_cl ? atoi(e_cl) : 0;
+    if (forced != 128 && forced != 256 && forced != 512 && forced != 1024) forced = 0;
+    if (forced_cl != 2 && forced_cl != 4 && forced_cl != 8) forced_cl = 0;
     int64_t widest = (int64_t)(p.ni - 1) * (p.nj - 1);           // upper bound on a level's node count
     int nt = widest >= 16384 ? 1024 : (widest >= 4096 ? 512 : (widest >= 2048 ? 256 : 128));
     // a batch too small to fill the GPU with small CTAs is latency-bound per mesh: give each mesh more threads,

@@ -48,14 +48,18 @@ def dfgen_geometry(dim, padding=0, is_unit_cube=1, bbox_min=None, bbox_max=None)
 _ws_cache = {}
 
 
-def _workspace(nbytes, device):
-    """Grow-only scratch per device, so steady-state calls never allocate."""
-    ws = _ws_cache.get(device)
+def _workspace(nbytes, device, stream):
+    """Grow-only scratch per (device, stream), so steady-state calls never allocate and two calls enqueued on
+    distinct streams never share scratch (thread-safe for distinct streams). A buffer that is outgrown is
+    handed back to torch's caching allocator, which keeps it alive until the work queued on it has drained."""
+    key = (device, stream)
+    ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = None
-        _ws_cache.pop(device, None)
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-        _ws_cache[device] = ws
+        old = _ws_cache.get(key)
+        if old is not None:
+            old.record_stream(torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.default_stream(device))
+        _ws_cache[key] = ws
     return ws
 
 
@@ -90,8 +94,8 @@ def tdf_batch_params(verts, vert_off, tris, tri_off, params, outputs=("sdf",), d
                 res[name] = torch.empty(shape, dtype=_DTYPES[name], device=device)
             setattr(o, name, res[name].data_ptr())
         nbytes = L.g3d_tdf_workspace_bytes(n_mesh, total_verts, total_tris, C.byref(params))
-        ws = _workspace(nbytes, device)
         stream = torch.cuda.current_stream(device).cuda_stream
+        ws = _workspace(nbytes, device, stream)
         _lib.check(L.g3d_tdf_batch(verts.data_ptr(), vert_off.data_ptr(), total_verts, tris.data_ptr(),
                                    tri_off.data_ptr(), total_tris, n_mesh, C.byref(params), C.byref(o),
                                    ws.data_ptr(), ws.numel(), stream))

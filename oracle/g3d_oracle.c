@@ -355,3 +355,27 @@ void g3d_oracle_brute_force(const uint32_t *tri, int64_t ntri, const float *x, c
                 if (closest_tri) closest_tri[q] = bt;
             }
 }
+
+/* The same minimum for a list of voxels only (linear indices i + ni*(j + nj*k)): lets the GPU tests spot-check grids
+ * whose full brute force would take hours on a CPU (128^3 x 200k triangles). */
+void g3d_oracle_brute_force_points(const uint32_t *tri, int64_t ntri, const float *x, const float *origin,
+                                   float dx, int ni, int nj, int nk, const int64_t *idx, int64_t nidx,
+                                   float *phi, int32_t *closest_tri)
+{
+    float far = (ni + nj + nk) * dx;
+    for (int64_t p = 0; p < nidx; ++p) {
+        int64_t q = idx[p];
+        int i = (int)(q % ni), j = (int)((q / ni) % nj), k = (int)(q / ((int64_t)ni * nj));
+        float gx[3] = { i * dx + origin[0], j * dx + origin[1], k * dx + origin[2] };
+        float best = far;
+        int32_t bt = -1;
+        for (int64_t t = 0; t < ntri; ++t) {
+            float d = g3d_oracle_point_triangle_distance(gx, x + 3 * (size_t)tri[3 * t],
+                                                         x + 3 * (size_t)tri[3 * t + 1],
+                                                         x + 3 * (size_t)tri[3 * t + 2]);
+            if (d < best) { best = d; bt = (int32_t)t; }
+        }
+        phi[p] = best;
+        if (closest_tri) closest_tri[p] = bt;
+    }
+}

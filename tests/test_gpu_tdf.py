@@ -486,3 +486,160 @@ def test_host_abi_submit_wait_pipeline(g3d):
     g3d.check(L.g3d_tdf_batch_host_submit(ctx, None, None, None, None, 0, C.byref(p), C.byref(batches[0][8]), C.byref(tk)))
     g3d.check(L.g3d_tdf_batch_host_wait(ctx, tk.value))
     L.g3d_context_destroy(ctx)
+
+
+# ---------------------------------------------------------------- BASELINE configs[0], [2], [3], [4] at full size
+
+@pytest.fixture(scope="module")
+def config3_case(oracle):
+    """BASELINE configs[3]: one 201,840-triangle table at 128^3. The reference itself (oracle/_ref, else the C port)
+    computes the expected field once per test session (~10 s of CPU)."""
+    v, t = S.table_mesh(58, seed=0)
+    g = oracle.dfgen_geometry(128)
+    if oracle.ref_available():
+        phi = oracle.ref_make_level_set3(t, v, g["origin"], g["dx"], 128, 128, 128)
+    else:
+        phi = oracle.make_level_set3(t, v, g["origin"], g["dx"], 128, 128, 128)["phi"]
+    return v, t, phi * np.float32(128)
+
+
+@pytest.mark.parametrize("cluster", [None, "2", "4", "8"])
+def test_config3_128cube_200k_tris_faithful_bit_equal(g3d, oracle, config3_case, cluster, monkeypatch):
+    """configs[3] (128^3 x 201,840 triangles), faithful mode, bit-equal to the reference's make_level_set3 with the
+    sweep's thread-block cluster size left to the library and forced to 2, 4 and 8 CTAs per mesh."""
+    from generate3d_b200 import dfgen
+    v, t, want = config3_case
+    assert len(t) == 201840
+    if cluster is None:
+        monkeypatch.delenv("G3D_SWEEP_CLUSTER", raising=False)
+    else:
+        monkeypatch.setenv("G3D_SWEEP_CLUSTER", cluster)
+    got = _run(dfgen, [(v, t)], 128, outputs=("sdf", "occ_f32", "status"))
+    assert got["status"][0] == 0
+    assert np.array_equal(_bits(got["sdf"][0]), _bits(want))
+    assert np.array_equal(got["occ_f32"][0].astype(np.uint8), oracle.occupancy(want))
+
+
+def test_config3_128cube_exact_mode_properties(g3d, oracle, config3_case):
+    """configs[3] in exact mode: a CPU brute force over 4.2e11 pairs is out of reach, so the size-independent
+    properties are checked instead: same signs, identical |d| <= 1 occupancy (the reference's band is exact there),
+    bit-equal distances inside that band, never larger than the reference's field within the truncation, and equal
+    to the brute-force oracle on a sample of 1,000 voxels."""
+    from generate3d_b200 import dfgen
+    v, t, want = config3_case
+    got = _run(dfgen, [(v, t)], 128, mode="exact", outputs=("sdf", "occ_f32", "closest_tri", "status"))
+    sdf = got["sdf"][0]
+    assert got["status"][0] == 0
+    assert np.array_equal(np.signbit(sdf), np.signbit(want))
+    assert np.array_equal(got["occ_f32"][0].astype(np.uint8), oracle.occupancy(want))
+    band1 = np.abs(want) <= 1.0
+    assert np.array_equal(_bits(sdf[band1]), _bits(want[band1]))
+    near = np.signbit(want) | (np.abs(sdf) <= 3.0)
+    assert np.all(np.abs(sdf)[near] <= np.abs(want)[near])
+    # sampled brute force (the reference's distance function over ALL triangles) on voxels of the band
+    rng = np.random.default_rng(7)
+    idx = np.flatnonzero(np.abs(want).ravel() <= 3.0)
+    pick = rng.choice(idx, 1000, replace=False)
+    g = oracle.dfgen_geometry(128)
+    bf, bt = oracle.brute_force_points(t, v, g["origin"], g["dx"], 128, 128, 128, pick)
+    assert np.array_equal(_bits(np.abs(sdf).ravel()[pick]), _bits(bf * np.float32(128)))
+    assert np.array_equal(got["closest_tri"][0].ravel()[pick], bt)
+
+
+@pytest.mark.parametrize("mode", ["faithful", "exact"])
+def test_config0_single_5k_mesh_both_modes(g3d, oracle, mode):
+    """configs[0]: one 4,860-triangle table at 32^3, truncation 3: sdf, tdf, tdflog and occupancy against the oracle
+    (faithful: everything bit-equal / 1e-5; exact: bit-equal to the brute force where it matters)."""
+    from generate3d_b200 import dfgen
+    v, t = S.table_mesh(9, seed=0)
+    assert len(t) == 4860
+    want = _oracle_full(oracle, v, t, 32)
+    got = _run(dfgen, [(v, t)], 32, mode=mode)
+    assert np.array_equal(got["occ_f32"][0].astype(np.uint8), oracle.occupancy(want["sdf"]))
+    if mode == "faithful":
+        assert np.array_equal(_bits(got["sdf"][0]), _bits(want["sdf"]))
+        tdf = oracle.load_df_clamp(want["sdf"], 3.0)
+        assert np.array_equal(_bits(got["tdf"][0]), _bits(tdf))
+        assert np.abs(got["tdflog"][0] - oracle.apply_log_transform(tdf)).max() <= 1e-5
+    else:
+        g = oracle.dfgen_geometry(32)
+        bf, bt = oracle.brute_force(t, v, g["origin"], g["dx"], 32, 32, 32)
+        near = np.signbit(want["sdf"]) | (bf * np.float32(32) <= 3.0)
+        assert np.array_equal(_bits(np.abs(got["sdf"][0])[near]), _bits((bf * np.float32(32))[near]))
+        assert np.array_equal(got["closest_tri"][0][near], bt[near])
+        assert np.abs(got["tdflog"][0][near] - oracle.apply_log_transform(oracle.load_df_clamp(
+            np.copysign(bf * np.float32(32), want["sdf"]), 3.0))[near]).max() <= 1e-5
+
+
+def test_config2_bench_batch_sampled_meshes_vs_reference(g3d, oracle):
+    """configs[2] at FULL size: the very batch bench.py times (1,024 tables x 19,440 triangles, seeds 0..1023), all
+    five outputs; 8 sampled meshes are compared bit for bit with the reference's make_level_set3, and the whole
+    batch must be free of error flags and equal to itself when solved a second time (determinism)."""
+    from generate3d_b200 import dfgen
+    V, voff, T, toff = S.table_batch(1024, 18, first_seed=0)
+    outs = ("sdf", "tdf", "tdflog", "occ_bits", "status")
+    r = dfgen.tdf_batch(V, voff, T, toff, outputs=outs)
+    torch.cuda.synchronize()
+    assert int(r["status"].sum().item()) == 0
+    sdf = r["sdf"].cpu().numpy()
+    bits = r["occ_bits"].cpu().numpy()
+    tdflog = r["tdflog"].cpu().numpy()
+    g = oracle.dfgen_geometry(32)
+    for m in (0, 1, 255, 256, 511, 700, 1022, 1023):
+        v, t = V[voff[m]:voff[m + 1]], T[toff[m]:toff[m + 1]]
+        if oracle.ref_available():
+            want = oracle.ref_make_level_set3(t, v, g["origin"], g["dx"], 32, 32, 32) * np.float32(32)
+        else:
+            want = _oracle_full(oracle, v, t, 32)["sdf"]
+        assert np.array_equal(_bits(sdf[m]), _bits(want)), m
+        occ = np.unpackbits(bits[m].view(np.uint8), bitorder="little").reshape(32, 32, 32)
+        assert np.array_equal(occ, oracle.occupancy(want)), m
+        assert np.abs(tdflog[m] - oracle.apply_log_transform(oracle.load_df_clamp(want, 3.0))).max() <= 1e-5, m
+    r2 = dfgen.tdf_batch(V, voff, T, toff, outputs=("sdf",))
+    assert torch.equal(r2["sdf"], r["sdf"])
+
+
+def test_config4_device_generated_shard_matches_host_path(g3d, oracle):
+    """configs[4] (dataset-scale generation, inputs generated on the device per shard from the model seed): a chunk
+    of the on-device generator, copied back, gives the same fields through the CPU reference; chunks are
+    independent of chunk size and of the rank that owns them."""
+    from generate3d_b200 import dataset_gen
+    dev = torch.device("cuda", 0)
+    a = dataset_gen.generate_tables(first_model=4000, count=6, n=18, device=dev)
+    b = dataset_gen.generate_tables(first_model=4003, count=3, n=18, device=dev)
+    nv = a["verts"].shape[0] // 6
+    assert torch.equal(a["verts"][3 * nv:], b["verts"])                      # a model depends on its index only
+    res = dataset_gen.voxelize_shard(first_model=4000, count=6, chunk=4, n=18, device=dev, keep=("sdf", "tdf", "occ_bits"))
+    assert int(res["status"].sum().item()) == 0 and res["sdf"].shape[0] == 6
+    V = a["verts"].cpu().numpy()
+    T = a["tris"].cpu().numpy().view(np.uint32)
+    g = oracle.dfgen_geometry(32)
+    nt = T.shape[0] // 6
+    for m in (0, 3, 5):
+        want = _oracle_full(oracle, V[m * nv:(m + 1) * nv], T[m * nt:(m + 1) * nt], 32)["sdf"]
+        assert np.array_equal(_bits(res["sdf"][m].cpu().numpy()), _bits(want)), m
+    lo, hi = dataset_gen.shard_models(100000, 3, 8)
+    assert (lo, hi) == (37500, 50000)
+
+
+def test_two_streams_do_not_share_scratch(g3d):
+    """the device ABI is thread-safe for distinct streams. Two batches enqueued back to back on two streams
+    (so that their kernels may interleave) give the results of the same batches solved one after the other."""
+    from generate3d_b200 import dfgen
+    A = S.table_batch(40, 6, first_seed=700)
+    B = S.table_batch(40, 6, first_seed=800)
+    ra = dfgen.tdf_batch(*A, outputs=("sdf", "closest_tri"))
+    rb = dfgen.tdf_batch(*B, outputs=("sdf", "closest_tri"))
+    torch.cuda.synchronize()
+    dA = [torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x).cuda() for x in A]
+    dB = [torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x).cuda() for x in B]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            qa = dfgen.tdf_batch(*dA, outputs=("sdf", "closest_tri"))
+        with torch.cuda.stream(s2):
+            qb = dfgen.tdf_batch(*dB, outputs=("sdf", "closest_tri"))
+    torch.cuda.synchronize()
+    assert torch.equal(qa["sdf"], ra["sdf"]) and torch.equal(qa["closest_tri"], ra["closest_tri"])
+    assert torch.equal(qb["sdf"], rb["sdf"]) and torch.equal(qb["closest_tri"], rb["closest_tri"])
