@@ -21,7 +21,7 @@ UNITS = {
     "g3d_raycast.cu": ["-fmad=false"],
     "g3d_next.cu": ["-fmad=false"],
     "g3d_capi.cu": [],
-    "g3d_mesh_io.cpp": [],
+    "g3d_mesh_io.cpp": ["-Xcompiler", "-ffp-contract=off"],      # replays tinyobj's double / float arithmetic
 }
 HEADERS = ["g3d_internal.h", "g3d_ptd.cuh", "g3d_tdf_exact.cuh", os.path.join("..", "..", "include", "g3d.h")]
 

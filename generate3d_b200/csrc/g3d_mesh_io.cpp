@@ -5,9 +5,10 @@
 // record is kept (also unreferenced ones, main.cpp:71-76 copies all columns),
 // faces are emitted in file order across groups, indices may be negative
 // (relative) and may carry /vt/vn suffixes -- and ASCII / binary little-endian
-// PLY with float x,y,z and a list face property. Triangle faces map 1:1.
-// Polygons with more than three corners are fan-triangulated (the reference's
-// tinyobj version ear-clips them; dfgen's usage text demands triangle meshes).
+// PLY with float x,y,z and a list face property. Numbers and polygons are
+// handled exactly as the vendored tinyobjloader handles them (see load_obj);
+// pinned against that header compiled in place (tests/test_mesh_io.py).
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,55 +28,298 @@ bool ends_with_ci(const std::string& s, const char* ext)
     return s.find(ext) != std::string::npos;       // LoaderMesh.h:16,53 uses find(), not a suffix test
 }
 
+// ---- Wavefront OBJ, with the observable behaviour of the tinyobjloader version the reference vendors
+// (src/utils/tiny_obj_loader.h) as load_mesh uses it (LoaderMesh.h:17-50: every attrib.vertices entry, the
+// vertex_index of every emitted corner, shapes in order). What has to match for a byte-identical .df:
+//   * numbers: tinyobj does not call strtod. Its parser (tiny_obj_loader.h:505-618) accumulates the integer digits
+//     in a double, adds each fraction digit times a table entry 1e-k (std::pow(10, -k) from the 8th digit on), and
+//     applies a decimal exponent as ldexp(m * 5^e, e); the double is then narrowed to float (:620-628). The result
+//     is NOT the correctly rounded float of the text in general, so the same arithmetic is replayed here;
+//     a token it cannot parse ("", ".5", "-.5", "nan") leaves the default 0;
+//   * lines end at LF, CRLF or a lone CR (:399-428);
+//   * face corners are read with atoi + strcspn (:754-806), so "3/ 4" and friends behave as there; index 0 (or a
+//     non-number) makes the whole load fail (:1668-1676; LoaderMesh.h:24 then asserts);
+//   * polygons with more than three corners are ear-clipped in the projection chosen from the first non-degenerate
+//     corner (:1011-1146), float arithmetic, at most ten trips round the polygon, ears emitted in discovery order;
+//     faces with fewer than three corners emit nothing;
+//   * faces are flushed into the current shape at `g`, `o`, a `usemtl` that changes the material id, and at the
+//     end (:1693-1911, 1939-1948). A shape whose faces were all flushed by `usemtl` before an `o` line is DROPPED
+//     by that version (`o` only keeps the shape when the pending group was non-empty); reproduced, which is why the
+//     material names of the mtllib files are read too (only their identity matters).
+double tinyobj_number(const char* s, const char* end, double fallback)
+{
+    if (s >= end) return fallback;
+    const char* c = s;
+    double sign = 1.0;
+    if (*c == '+' || *c == '-') { if (*c == '-') sign = -1.0; ++c; }
+    else if (!(*c >= '0' && *c <= '9')) return fallback;
+    double m = 0.0;
+    int nread = 0;
+    while (c != end && *c >= '0' && *c <= '9') { m *= 10; m += (int)(*c - '0'); ++c; ++nread; }
+    if (nread == 0) return fallback;
+    int ex = 0;
+    bool at_end = (c == end);
+    if (!at_end) {
+        if (*c == '.') {
+            static const double frac[] = { 1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001 };
+            ++c;
+            int k = 1;
+            while (c != end && *c >= '0' && *c <= '9') {
+                m += (int)(*c - '0') * (k < 8 ? frac[k] : pow(10.0, -k));
+                ++k;
+                ++c;
+            }
+            at_end = (c == end);
+        } else if (*c != 'e' && *c != 'E') {
+            at_end = true;                                  // anything else ends the number
+        }
+        if (!at_end && (*c == 'e' || *c == 'E')) {
+            ++c;
+            bool neg = false;
+            if (c != end && (*c == '+' || *c == '-')) { neg = (*c == '-'); ++c; }
+            else if (!(*c >= '0' && *c <= '9')) return fallback;       // an empty exponent is a parse failure
+            int nd = 0;
+            while (c != end && *c >= '0' && *c <= '9') { ex *= 10; ex += (int)(*c - '0'); ++c; ++nd; }
+            if (neg) ex = -ex;
+            if (nd == 0) return fallback;
+        }
+    }
+    return sign * (ex ? ldexp(m * pow(5.0, ex), ex) : m);
+}
+
+float tinyobj_real(const char*& p)
+{
+    p += strspn(p, " \t");
+    const char* end = p + strcspn(p, " \t\r");
+    const float f = (float)tinyobj_number(p, end, 0.0);
+    p = end;
+    return f;
+}
+
+// 1-based -> 0-based, negative = relative to the `n` records seen so far; 0 is invalid
+bool obj_index(int idx, long long n, long long& out)
+{
+    if (idx > 0) { out = idx - 1; return true; }
+    if (idx < 0) { out = n + idx; return true; }
+    return false;
+}
+
+// one face corner "i", "i/j", "i//k", "i/j/k": only the vertex index is kept, but every field must be valid
+bool obj_corner(const char*& p, long long nv, long long nvn, long long nvt, long long& vi)
+{
+    long long dummy;
+    if (!obj_index(atoi(p), nv, vi)) return false;
+    p += strcspn(p, "/ \t\r");
+    if (p[0] != '/') return true;
+    ++p;
+    if (p[0] == '/') {                                       // i//k
+        ++p;
+        if (!obj_index(atoi(p), nvn, dummy)) return false;
+        p += strcspn(p, "/ \t\r");
+        return true;
+    }
+    if (!obj_index(atoi(p), nvt, dummy)) return false;       // i/j or i/j/k
+    p += strcspn(p, "/ \t\r");
+    if (p[0] != '/') return true;
+    ++p;
+    if (!obj_index(atoi(p), nvn, dummy)) return false;
+    p += strcspn(p, "/ \t\r");
+    return true;
+}
+
+int crossing_parity(const float* vx, const float* vy, float tx, float ty)       // point in the triangle (vx, vy)?
+{
+    int c = 0;
+    for (int i = 0, j = 2; i < 3; j = i++)
+        if (((vy[i] > ty) != (vy[j] > ty)) && (tx < (vx[j] - vx[i]) * (ty - vy[i]) / (vy[j] - vy[i]) + vx[i])) c = !c;
+    return c;
+}
+
+// Ear clipping of one polygon as tiny_obj_loader.h:1011-1146 does it. `v` holds the vertices read SO FAR (the
+// reference triangulates at flush time); a corner outside that range is undefined behaviour there and flagged here.
+void emit_face(const std::vector<long long>& face, const std::vector<float>& v, std::vector<uint32_t>& out)
+{
+    const size_t n = face.size();
+    auto put = [&](long long a) { out.push_back((a < 0 || a > 0xfffffffell) ? 0xffffffffu : (uint32_t)a); };
+    if (n < 3) return;
+    if (n == 3) { put(face[0]); put(face[1]); put(face[2]); return; }
+    const long long nv = (long long)v.size() / 3;
+    for (long long a : face)
+        if (a < 0 || a >= nv) {                              // cannot be triangulated: emit a fan of flagged corners
+            for (size_t k = 2; k < n; ++k) { put(-1); put(-1); put(-1); }
+            return;
+        }
+    auto X = [&](long long a, size_t ax) { return v[(size_t)a * 3 + ax]; };
+    size_t ax0 = 1, ax1 = 2;
+    for (size_t k = 0; k < n; ++k) {
+        const long long a = face[k % n], b = face[(k + 1) % n], c = face[(k + 2) % n];
+        const float e0x = X(b, 0) - X(a, 0), e0y = X(b, 1) - X(a, 1), e0z = X(b, 2) - X(a, 2);
+        const float e1x = X(c, 0) - X(b, 0), e1y = X(c, 1) - X(b, 1), e1z = X(c, 2) - X(b, 2);
+        const float cx = fabsf(e0y * e1z - e0z * e1y), cy = fabsf(e0z * e1x - e0x * e1z), cz = fabsf(e0x * e1y - e0y * e1x);
+        const float eps = 0.0001f;
+        if (cx > eps || cy > eps || cz > eps) {
+            if (!(cx > cy && cx > cz)) {
+                ax0 = 0;
+                if (cz > cx && cz > cy) ax1 = 1;
+            }
+            break;
+        }
+    }
+    float area = 0;
+    for (size_t k = 0; k < n; ++k) {
+        const long long a = face[k % n], b = face[(k + 1) % n];
+        area += (X(a, ax0) * X(b, ax1) - X(a, ax1) * X(b, ax0)) * 0.5f;
+    }
+    std::vector<long long> rest(face);
+    int rounds = 10;
+    size_t guess = 0;
+    while (rest.size() > 3 && rounds > 0) {
+        const size_t m = rest.size();
+        if (guess >= m) { --rounds; guess -= m; }
+        long long ind[3];
+        float vx[3], vy[3];
+        for (size_t k = 0; k < 3; ++k) {
+            ind[k] = rest[(guess + k) % m];
+            vx[k] = X(ind[k], ax0);
+            vy[k] = X(ind[k], ax1);
+        }
+        const float e0x = vx[1] - vx[0], e0y = vy[1] - vy[0], e1x = vx[2] - vx[1], e1y = vy[2] - vy[1];
+        const float cross = e0x * e1y - e0y * e1x;
+        if (cross * area < 0.0f) { ++guess; continue; }      // a reflex corner
+        bool overlap = false;
+        for (size_t o = 3; o < m; ++o) {
+            const long long q = rest[(guess + o) % m];
+            if (crossing_parity(vx, vy, X(q, ax0), X(q, ax1))) { overlap = true; break; }
+        }
+        if (overlap) { ++guess; continue; }
+        put(ind[0]); put(ind[1]); put(ind[2]);               // an ear
+        rest.erase(rest.begin() + (long)((guess + 1) % m));
+    }
+    if (rest.size() == 3) { put(rest[0]); put(rest[1]); put(rest[2]); }
+}
+
+// names of the materials of one .mtl file, in tinyobj's numbering (tiny_obj_loader.h:1206-1262, 1570-1574):
+// a material is registered when the next `newmtl` comes (unless its name is empty) and once more at the end
+void read_mtl_names(FILE* fp, std::vector<std::string>& names, int& n_materials)
+{
+    std::string line, cur;
+    int c;
+    auto reg = [&](const std::string& nm) {
+        bool have = false;
+        for (size_t i = 0; i < names.size(); i += 1) if (names[i] == nm) { have = true; break; }
+        (void)have;
+        names.push_back(nm);                                 // slot index = material id (first definition wins on lookup)
+        ++n_materials;
+    };
+    for (;;) {
+        line.clear();
+        bool eof = false;
+        for (;;) {
+            c = fgetc(fp);
+            if (c == EOF) { eof = true; break; }
+            if (c == '\n') break;
+            if (c == '\r') { int d = fgetc(fp); if (d != '\n' && d != EOF) ungetc(d, fp); break; }
+            line.push_back((char)c);
+        }
+        if (eof && line.empty()) break;
+        const size_t last = line.find_last_not_of(" \t");
+        line = (last == std::string::npos) ? std::string() : line.substr(0, last + 1);
+        const char* p = line.c_str();
+        p += strspn(p, " \t");
+        if (strncmp(p, "newmtl", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+            if (!cur.empty()) reg(cur);
+            cur = std::string(p + 7);
+        }
+        if (eof) break;
+    }
+    reg(cur);
+}
+
 int load_obj(const char* path, std::vector<float>& v, std::vector<uint32_t>& f)
 {
     FILE* fp = fopen(path, "rb");
     if (!fp) { g3d::set_error("load_mesh: cannot open %s", path); return G3D_ERR_IO; }
-    std::vector<char> line;
-    std::vector<long long> corner;
-    int c;
+    std::string dir(path);
+    dir = dir.substr(0, dir.rfind('/') + 1);                 // LoaderMesh.h:21 (npos + 1 == 0: empty prefix)
+    std::vector<std::string> mat_names;                      // index = material id
+    int n_materials = 0, material = -1;
+    long long nvn = 0, nvt = 0;
+    std::vector<std::vector<long long> > group;              // faces waiting to be flushed into the shape
+    std::vector<uint32_t> shape;                             // corners of the current shape
+    std::string line;
     bool bad = false;
-    for (;;) {
+    auto flush = [&]() -> bool {
+        if (group.empty()) return false;
+        for (const auto& face : group) emit_face(face, v, shape);
+        return true;
+    };
+    auto keep_shape = [&]() { f.insert(f.end(), shape.begin(), shape.end()); };
+    for (bool eof = false; !eof && !bad;) {
         line.clear();
-        while ((c = fgetc(fp)) != EOF && c != '\n') line.push_back((char)c);
-        if (c == EOF && line.empty()) break;
-        line.push_back('\0');
-        const char* p = line.data();
-        while (*p == ' ' || *p == '\t') ++p;
-        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
-            char* e = nullptr;
-            p += 2;
-            for (int k = 0; k < 3; ++k) {
-                float x = strtof(p, &e);
-                if (e == p) x = 0.f;               // tinyobj's parseReal defaults to 0
-                v.push_back(x);
-                p = e;
-            }
-        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
-            p += 2;
-            corner.clear();
-            const long long nv = (long long)v.size() / 3;
-            for (;;) {
-                while (*p == ' ' || *p == '\t' || *p == '\r') ++p;
-                if (!*p) break;
-                char* e = nullptr;
-                long long idx = strtoll(p, &e, 10);
-                if (e == p) { bad = true; break; }
-                // tinyobj fixIndex: 1-based, negative = relative to the vertices seen so far
-                long long vi = idx > 0 ? idx - 1 : (idx < 0 ? nv + idx : -1);
-                corner.push_back(vi);
-                p = e;
-                while (*p && *p != ' ' && *p != '\t' && *p != '\r') ++p;   // skip /vt/vn
-            }
-            for (size_t k = 2; k < corner.size(); ++k) {
-                long long t[3] = { corner[0], corner[k - 1], corner[k] };
-                for (int q = 0; q < 3; ++q) f.push_back(t[q] < 0 ? 0xffffffffu : (uint32_t)t[q]);
-            }
+        for (;;) {
+            const int c = fgetc(fp);
+            if (c == EOF) { eof = true; break; }
+            if (c == '\n') break;
+            if (c == '\r') { const int d = fgetc(fp); if (d != '\n' && d != EOF) ungetc(d, fp); break; }
+            line.push_back((char)c);
         }
-        if (c == EOF) break;
+        // an embedded NUL ends the line for tinyobj's C-string scanning as well (c_str())
+        const char* p = line.c_str();
+        p += strspn(p, " \t");
+        if (p[0] == '\0' || p[0] == '#') continue;
+        const bool sp1 = (p[1] == ' ' || p[1] == '\t'), sp2 = p[1] && (p[2] == ' ' || p[2] == '\t');
+        if (p[0] == 'v' && sp1) {
+            p += 2;
+            const float x = tinyobj_real(p), y = tinyobj_real(p), z = tinyobj_real(p);
+            v.push_back(x); v.push_back(y); v.push_back(z);
+        } else if (p[0] == 'v' && p[1] == 'n' && sp2) {
+            ++nvn;
+        } else if (p[0] == 'v' && p[1] == 't' && sp2) {
+            ++nvt;
+        } else if (p[0] == 'f' && sp1) {
+            p += 2;
+            p += strspn(p, " \t");
+            std::vector<long long> face;
+            while (!(p[0] == '\r' || p[0] == '\n' || p[0] == '\0')) {
+                long long vi;
+                if (!obj_corner(p, (long long)v.size() / 3, nvn, nvt, vi)) { bad = true; break; }
+                face.push_back(vi);
+                p += strspn(p, " \t\r");
+            }
+            if (!bad) group.push_back(face);
+        } else if (strncmp(p, "usemtl", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+            const std::string name(p + 7);
+            int id = -1;
+            for (size_t i = 0; i < mat_names.size(); ++i) if (mat_names[i] == name) { id = (int)i; break; }
+            if (id != material) {
+                flush();
+                group.clear();
+                material = id;
+            }
+        } else if (strncmp(p, "mtllib", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+            std::stringstream ss{ std::string(p + 7) };
+            std::string item;
+            while (std::getline(ss, item, ' ')) {              // first file that opens wins (:1713-1727)
+                FILE* mf = fopen((dir + item).c_str(), "rb");
+                if (!mf) continue;
+                read_mtl_names(mf, mat_names, n_materials);
+                fclose(mf);
+                break;
+            }
+        } else if (p[0] == 'g' && sp1) {
+            flush();
+            if (!shape.empty()) keep_shape();
+            shape.clear();
+            group.clear();
+        } else if (p[0] == 'o' && sp1) {
+            if (flush()) keep_shape();                         // sic: a shape filled only by usemtl flushes is dropped
+            shape.clear();
+            group.clear();
+        }
     }
     fclose(fp);
-    if (bad) { g3d::set_error("load_mesh: malformed face record in %s", path); return G3D_ERR_IO; }
+    if (bad) { g3d::set_error("load_mesh: failed to parse an `f' line of %s (e.g. zero value for a face index)", path); return G3D_ERR_IO; }
+    if (flush() || !shape.empty()) keep_shape();
     return G3D_OK;
 }
 
