@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libg3d_b200.so")
 
 G3D_OK = 0
 MODE_FAITHFUL, MODE_EXACT = 0, 1
-MESH_BAD_INDEX, MESH_EMPTY = 1, 2
+MESH_BAD_INDEX, MESH_EMPTY, MESH_TOO_MANY_TRIS = 1, 2, 4
 
 
 class TdfParams(C.Structure):
@@ -63,6 +63,9 @@ SYMBOLS = {
     "g3d_profile_enable": (C.c_int, [_i32]),
     "g3d_profile_read": (C.c_int, [_vp, _vp]),
     "g3d_probe_fp32_tflops": (C.c_int, [_vp, _vp]),
+    "g3d_host_alloc": (_vp, [_sz]),
+    "g3d_host_free": (None, [_vp]),
+    "g3d_vox2mesh": (C.c_int, [C.c_char_p, C.c_char_p, _i32, _i32, C.c_char_p, _f32, _i32]),
     "g3d_load_mesh": (C.c_int, [C.c_char_p, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
                                 C.POINTER(_i64)]),
     "g3d_free": (None, [_vp]),

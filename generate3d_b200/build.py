@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libg3d_b200.so")
 CLI = os.path.join(HERE, "bin", "dfgen")
+VOX2MESH = os.path.join(HERE, "bin", "vox2mesh")
+CLIS = {CLI: "dfgen_main.cpp", VOX2MESH: "vox2mesh_main.cpp"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 UNITS = {
@@ -36,21 +38,25 @@ def _stale(target, sources):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    objs = []
+    objs, cmds = [], []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
-            subprocess.check_call(cmd)
+            cmds.append([nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
         objs.append(o)
+    if cmds:                                                   # the translation units are independent: compile side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(cmds)) as ex:
+            list(ex.map(subprocess.check_call, cmds))
     if force or _stale(LIB, objs):
         subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", LIB] + objs)
-    cli_src = os.path.join(CSRC, "dfgen_main.cpp")
-    if os.path.exists(cli_src) and (force or _stale(CLI, [cli_src, LIB] + hdrs)):
-        os.makedirs(os.path.dirname(CLI), exist_ok=True)
-        subprocess.check_call([nvcc] + ARCH + ["-O2", "-std=c++17", "-o", CLI, cli_src, "-L" + HERE, "-lg3d_b200",
-                                               "-Xlinker", "-rpath,$ORIGIN/.."])
+    for exe, src_name in CLIS.items():                         # the reference's two executables, same argv
+        cli_src = os.path.join(CSRC, src_name)
+        if os.path.exists(cli_src) and (force or _stale(exe, [cli_src, LIB] + hdrs)):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            subprocess.check_call([nvcc] + ARCH + ["-O2", "-std=c++17", "-o", exe, cli_src, "-L" + HERE, "-lg3d_b200",
+                                                   "-Xcompiler", "-pthread", "-Xlinker", "-rpath,$ORIGIN/.."])
     return LIB
 
 

@@ -110,19 +110,22 @@ struct g3d_context {
 
 namespace {
 
-// grow-only device arena per slot; returns nullptr on failure (error already set)
+// Grow-only device arena per slot, from the stream-ordered allocator: growing a slot's arena neither synchronises
+// the device nor disturbs the other slot's batch in flight (cudaFree would do both). The slot itself is idle when
+// it grows (its previous batch has been waited for), so its old block is released in order on the kernel stream
+// and the new one is allocated on the input stream, which every later use of the slot is ordered after.
+// Returns nullptr on failure (error already set).
 char* arena_reserve(g3d_context* c, size_t bytes, int slot = 0)
 {
     if (bytes <= c->arena_bytes[slot]) return c->arena[slot];
     if (c->arena[slot]) {
-        cudaDeviceSynchronize();                    // the other slot may be in flight; cudaFree synchronises anyway
-        cudaFree(c->arena[slot]);
+        cudaFreeAsync(c->arena[slot], c->stream);
         c->arena[slot] = nullptr;
         c->arena_bytes[slot] = 0;
     }
     size_t want = align_up(bytes + bytes / 8, (size_t)1 << 20);
-    cudaError_t e = cudaMalloc((void**)&c->arena[slot], want);
-    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc(arena)"); return nullptr; }
+    cudaError_t e = cudaMallocAsync((void**)&c->arena[slot], want, c->s_in);
+    if (e != cudaSuccess) { c->arena[slot] = nullptr; cuda_fail(e, "cudaMallocAsync(arena)"); return nullptr; }
     c->arena_bytes[slot] = want;
     return c->arena[slot];
 }
@@ -273,6 +276,13 @@ int g3d_context_create(int32_t device, g3d_context** ctx)
     G3D_CUDA_TRY(cudaSetDevice(device));
     g3d_context* c = new g3d_context();
     c->device = device;
+    {   // blocks the arenas hand back stay cached in the device's pool instead of returning to the driver at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
@@ -295,13 +305,14 @@ void g3d_context_destroy(g3d_context* c)
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
     if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }
+    cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) {
         for (int i = 0; i < kHostChunks; ++i) {
             if (c->ev_in[b][i]) cudaEventDestroy(c->ev_in[b][i]);
             if (c->ev_fin[b][i]) cudaEventDestroy(c->ev_fin[b][i]);
         }
         if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]);
-        if (c->arena[b]) cudaFree(c->arena[b]);
+        if (c->arena[b]) cudaFreeAsync(c->arena[b], nullptr);
     }
     delete c;
 }
@@ -364,24 +375,27 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
     cudaStream_t s = c->stream;
     cudaEvent_t* ev_in = c->ev_in[slot];
     cudaEvent_t* ev_fin = c->ev_fin[slot];
+    // from here on work is enqueued: every failure path drains the three streams before returning, so that no copy is
+    // still running into the caller's arrays (or the arena) after the call has reported an error
     auto bail = [&](int code) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(c->s_out); return code; };
+#define G3D_TRY_BAIL(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(g3d::cuda_fail(e__, #expr)); } while (0)
     const int nch = n_mesh >= 64 ? kHostChunks : 1;
     auto chunk_lo = [&](int ch) { return (int)((int64_t)n_mesh * ch / nch); };
-    G3D_CUDA_TRY(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
-    G3D_CUDA_TRY(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
+    G3D_TRY_BAIL(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
+    G3D_TRY_BAIL(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
     for (int ch = 0; ch < nch; ++ch) {
         const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1);
         const int64_t v0 = vert_off[m0], v1 = vert_off[m1], t0 = tri_off[m0], t1 = tri_off[m1];
-        if (v1 > v0) G3D_CUDA_TRY(cudaMemcpyAsync(dv + 3 * v0, verts + 3 * v0, (size_t)(v1 - v0) * 12, cudaMemcpyHostToDevice, c->s_in));
-        if (t1 > t0) G3D_CUDA_TRY(cudaMemcpyAsync(dt + 3 * t0, tris + 3 * t0, (size_t)(t1 - t0) * 12, cudaMemcpyHostToDevice, c->s_in));
-        G3D_CUDA_TRY(cudaEventRecord(ev_in[ch], c->s_in));
+        if (v1 > v0) G3D_TRY_BAIL(cudaMemcpyAsync(dv + 3 * v0, verts + 3 * v0, (size_t)(v1 - v0) * 12, cudaMemcpyHostToDevice, c->s_in));
+        if (t1 > t0) G3D_TRY_BAIL(cudaMemcpyAsync(dt + 3 * t0, tris + 3 * t0, (size_t)(t1 - t0) * 12, cudaMemcpyHostToDevice, c->s_in));
+        G3D_TRY_BAIL(cudaEventRecord(ev_in[ch], c->s_in));
     }
-    G3D_CUDA_TRY(cudaStreamWaitEvent(s, ev_in[0], 0));           // the offset arrays precede chunk 0 on the input stream
+    G3D_TRY_BAIL(cudaStreamWaitEvent(s, ev_in[0], 0));           // the offset arrays precede chunk 0 on the input stream
     int rc = tdf_begin(nv, nt, n_mesh, *params, d, ws, ws_bytes, s);
     if (rc != G3D_OK) return bail(rc);
     for (int ch = 0; ch < nch; ++ch) {
         const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1);
-        G3D_CUDA_TRY(cudaStreamWaitEvent(s, ev_in[ch], 0));
+        G3D_TRY_BAIL(cudaStreamWaitEvent(s, ev_in[ch], 0));
         rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], m0, m1, nt, n_mesh, *params, d, ws, s);
         if (rc != G3D_OK) return bail(rc);
     }
@@ -392,21 +406,22 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
         const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1), nm = m1 - m0;
         rc = tdf_finalize(dvo, dto, nt, n_mesh, m0, m1, *params, d, ws, s);
         if (rc != G3D_OK) return bail(rc);
-        G3D_CUDA_TRY(cudaEventRecord(ev_fin[ch], s));
-        G3D_CUDA_TRY(cudaStreamWaitEvent(c->s_out, ev_fin[ch], 0));
+        G3D_TRY_BAIL(cudaEventRecord(ev_fin[ch], s));
+        G3D_TRY_BAIL(cudaStreamWaitEvent(c->s_out, ev_fin[ch], 0));
         const size_t gb = (size_t)nm * gv * 4, go = (size_t)m0 * gv;
-        if (out->sdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->sdf + go, d.sdf + go, gb, cudaMemcpyDeviceToHost, c->s_out));
-        if (out->tdf) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdf + go, d.tdf + go, gb, cudaMemcpyDeviceToHost, c->s_out));
-        if (out->tdflog) G3D_CUDA_TRY(cudaMemcpyAsync(out->tdflog + go, d.tdflog + go, gb, cudaMemcpyDeviceToHost, c->s_out));
-        if (out->occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_bits + (size_t)m0 * pw, d.occ_bits + (size_t)m0 * pw, (size_t)nm * pw * 4, cudaMemcpyDeviceToHost, c->s_out));
-        if (out->occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(out->occ_f32 + go, d.occ_f32 + go, gb, cudaMemcpyDeviceToHost, c->s_out));
-        if (out->closest_tri) G3D_CUDA_TRY(cudaMemcpyAsync(out->closest_tri + go, d.closest_tri + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->sdf) G3D_TRY_BAIL(cudaMemcpyAsync(out->sdf + go, d.sdf + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->tdf) G3D_TRY_BAIL(cudaMemcpyAsync(out->tdf + go, d.tdf + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->tdflog) G3D_TRY_BAIL(cudaMemcpyAsync(out->tdflog + go, d.tdflog + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->occ_bits) G3D_TRY_BAIL(cudaMemcpyAsync(out->occ_bits + (size_t)m0 * pw, d.occ_bits + (size_t)m0 * pw, (size_t)nm * pw * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->occ_f32) G3D_TRY_BAIL(cudaMemcpyAsync(out->occ_f32 + go, d.occ_f32 + go, gb, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->closest_tri) G3D_TRY_BAIL(cudaMemcpyAsync(out->closest_tri + go, d.closest_tri + go, gb, cudaMemcpyDeviceToHost, c->s_out));
     }
-    if (out->status) G3D_CUDA_TRY(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, c->s_out));
-    G3D_CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_out));
+    if (out->status) G3D_TRY_BAIL(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, c->s_out));
+    G3D_TRY_BAIL(cudaEventRecord(c->ev_done[slot], c->s_out));
     c->busy[slot] = true;
     *ticket = slot;
     return G3D_OK;
+#undef G3D_TRY_BAIL
 }
 
 int g3d_tdf_batch_host_wait(g3d_context* c, int32_t ticket)
@@ -455,17 +470,51 @@ int g3d_raycast_batch_host(g3d_context* c, const uint8_t* depth, const float* po
     char* base = arena_reserve(c, need);
     if (!base) return G3D_ERR_CUDA;
     layout(base, dd, dp, db, df, di);
+    // The depth images are the bulk of the traffic (H*W bytes per view against dim^3/8 bytes of result), so the call
+    // is bound by the host->device copy. The views cross PCIe in chunks on the input stream; a chunk's kernel starts
+    // when the chunk has landed and its results leave on the output stream while later chunks are still arriving:
+    // total time = the copy of the depth bytes + the tail of the last chunk.
     cudaStream_t s = c->stream;
-    G3D_CUDA_TRY(cudaMemcpyAsync(dd, depth, img, cudaMemcpyHostToDevice, s));
-    G3D_CUDA_TRY(cudaMemcpyAsync(dp, pose, (size_t)n_view * 64, cudaMemcpyHostToDevice, s));
-    int rc = g3d_raycast_batch(dd, dp, n_view, H, W, focal, cx, cy, clamp_max, dim, db, df, di, s);
-    if (rc != G3D_OK) return rc;
-    if (occ_bits) G3D_CUDA_TRY(cudaMemcpyAsync(occ_bits, db, (size_t)n_view * pw * 4, cudaMemcpyDeviceToHost, s));
-    if (occ_f32) G3D_CUDA_TRY(cudaMemcpyAsync(occ_f32, df, (size_t)n_view * nvox * 4, cudaMemcpyDeviceToHost, s));
-    if (index_map) G3D_CUDA_TRY(cudaMemcpyAsync(index_map, di, (size_t)n_view * 4 * nvox * 8, cudaMemcpyDeviceToHost, s));
-    G3D_CUDA_TRY(cudaStreamSynchronize(s));
+    auto bail = [&](int code) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(c->s_out); return code; };
+#define G3D_TRY_BAIL(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(g3d::cuda_fail(e__, #expr)); } while (0)
+    const int nch = n_view >= 2 * kHostChunks ? kHostChunks * 2 : 1;
+    const size_t per = (size_t)H * W;
+    cudaEvent_t* ev_in = c->ev_in[0];              // 2 x kHostChunks events per direction: both slots' sets
+    cudaEvent_t* ev_fin = c->ev_fin[0];
+    G3D_TRY_BAIL(cudaMemcpyAsync(dp, pose, (size_t)n_view * 64, cudaMemcpyHostToDevice, c->s_in));
+    for (int ch = 0; ch < nch; ++ch) {
+        const int v0 = (int)((int64_t)n_view * ch / nch), v1 = (int)((int64_t)n_view * (ch + 1) / nch);
+        G3D_TRY_BAIL(cudaMemcpyAsync(dd + v0 * per, depth + v0 * per, (size_t)(v1 - v0) * per, cudaMemcpyHostToDevice, c->s_in));
+        cudaEvent_t ein = ch < kHostChunks ? ev_in[ch] : c->ev_in[1][ch - kHostChunks];
+        cudaEvent_t efin = ch < kHostChunks ? ev_fin[ch] : c->ev_fin[1][ch - kHostChunks];
+        G3D_TRY_BAIL(cudaEventRecord(ein, c->s_in));
+        G3D_TRY_BAIL(cudaStreamWaitEvent(s, ein, 0));
+        int rc = g3d_raycast_batch(dd + v0 * per, dp + (size_t)v0 * 16, v1 - v0, H, W, focal, cx, cy, clamp_max, dim,
+                                   db ? db + (size_t)v0 * pw : nullptr, df ? df + (size_t)v0 * nvox : nullptr,
+                                   di ? di + (size_t)v0 * 4 * nvox : nullptr, s);
+        if (rc != G3D_OK) return bail(rc);
+        G3D_TRY_BAIL(cudaEventRecord(efin, s));
+        G3D_TRY_BAIL(cudaStreamWaitEvent(c->s_out, efin, 0));
+        const size_t nv = (size_t)(v1 - v0);
+        if (occ_bits) G3D_TRY_BAIL(cudaMemcpyAsync(occ_bits + (size_t)v0 * pw, db + (size_t)v0 * pw, nv * pw * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (occ_f32) G3D_TRY_BAIL(cudaMemcpyAsync(occ_f32 + (size_t)v0 * nvox, df + (size_t)v0 * nvox, nv * nvox * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (index_map) G3D_TRY_BAIL(cudaMemcpyAsync(index_map + (size_t)v0 * 4 * nvox, di + (size_t)v0 * 4 * nvox, nv * 4 * nvox * 8, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    G3D_TRY_BAIL(cudaStreamSynchronize(c->s_out));
+    G3D_TRY_BAIL(cudaStreamSynchronize(s));
+#undef G3D_TRY_BAIL
     return G3D_OK;
 }
+
+void* g3d_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc"); return nullptr; }
+    return p;
+}
+
+void g3d_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ----------------------------------------------------------- dfgen driver ----
 int g3d_dfgen_geometry(int32_t dim, int32_t padding, int32_t is_unit_cube, const float* bbox_min,
@@ -527,8 +576,10 @@ int g3d_read_df(const char* path, int32_t* dims, float* res, float* g2w, float* 
     if (ok && res) *res = r;
     if (ok && g2w) memcpy(g2w, m, sizeof m);
     if (ok && sdf) {
-        int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
-        if (dims[0] < 0 || dims[1] < 0 || dims[2] < 0 || n > capacity) {
+        // header values are untrusted: bound each dimension before multiplying (three large dims would wrap the product)
+        const bool sane = dims[0] >= 0 && dims[1] >= 0 && dims[2] >= 0 && dims[0] <= 65536 && dims[1] <= 65536 && dims[2] <= 65536;
+        int64_t n = sane ? (int64_t)dims[0] * dims[1] * dims[2] : -1;          // <= 2^48
+        if (!sane || capacity < 0 || n > capacity) {
             fclose(f);
             set_error("read_df: %s holds %lld values, capacity %lld", path, (long long)n, (long long)capacity);
             return G3D_ERR_INVALID;

@@ -425,3 +425,136 @@ extern "C" int g3d_load_mesh(const char* path, float** verts, int64_t* n_vert, u
 }
 
 extern "C" void g3d_free(void* p) { free(p); }
+
+// ------------------------------------------------------------------------------------------ vox2mesh ----
+namespace {
+
+// Colormap.h:1301-1325 with T = float (the `0.25 * dv` style terms are double arithmetic there, kept so)
+void jet_color(float v, float c[3])
+{
+    const float vmin = (float)-0.2, vmax = (float)1.0;
+    c[0] = c[1] = c[2] = 1.0f;
+    if (v < vmin) v = vmin;
+    if (v > vmax) v = vmax;
+    const float dv = vmax - vmin;
+    if (v < (vmin + 0.25 * dv)) {
+        c[0] = 0;
+        c[1] = 4 * (v - vmin) / dv;
+    } else if (v < (vmin + 0.5 * dv)) {
+        c[0] = 0;
+        c[2] = (float)(1 + 4 * (vmin + 0.25 * dv - v) / dv);
+    } else if (v < (vmin + 0.75 * dv)) {
+        c[0] = (float)(4 * (v - vmin - 0.5 * dv) / dv);
+        c[2] = 0;
+    } else {
+        c[1] = (float)(1 + 4 * (vmin + 0.75 * dv - v) / dv);
+        c[2] = 0;
+    }
+}
+
+// "%g" is what `ostream << float` prints with the default precision of 6 in the "C" locale (tinyply.h:452,616-617)
+void put_float(std::string& out, float x)
+{
+    char buf[32];
+    snprintf(buf, sizeof buf, "%g ", (double)x);
+    out += buf;
+}
+
+}  // namespace
+
+extern "C" int g3d_vox2mesh(const char* in_df, const char* out_ply, int32_t is_unitless, int32_t redcenter,
+                            const char* cmap, float trunc, int32_t write_ply)
+{
+    if (!in_df || !out_ply) { g3d::set_error("vox2mesh: NULL path"); return G3D_ERR_INVALID; }
+    if (cmap && strcmp(cmap, "jet") != 0) { g3d::set_error("vox2mesh: colour map '%s' is not carried (only jet)", cmap); return G3D_ERR_INVALID; }
+    std::string txt(out_ply);
+    const size_t dot = txt.rfind('.');
+    if (dot == std::string::npos) { g3d::set_error("vox2mesh: output name '%s' has no extension (the reference throws here, main.cpp:196)", out_ply); return G3D_ERR_INVALID; }
+    txt.replace(dot, 4, ".txt");                               // main.cpp:195-196
+    // load_vox (LoaderVOX.h:20-46): header, sdf, optional pdf
+    FILE* f = fopen(in_df, "rb");
+    if (!f) { g3d::set_error("vox2mesh: cannot open %s", in_df); return G3D_ERR_IO; }
+    int32_t dims[3];
+    float res = 0.f, g2w[16];
+    bool ok = fread(dims, 4, 3, f) == 3 && fread(&res, 4, 1, f) == 1 && fread(g2w, 4, 16, f) == 16;
+    if (!ok || dims[0] < 0 || dims[1] < 0 || dims[2] < 0 || dims[0] > 65536 || dims[1] > 65536 || dims[2] > 65536 ||
+        (int64_t)dims[0] * dims[1] * dims[2] > ((int64_t)1 << 31)) {
+        fclose(f);
+        g3d::set_error("vox2mesh: %s is not a .df file", in_df);
+        return G3D_ERR_IO;
+    }
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    std::vector<float> sdf(n), pdf;
+    ok = fread(sdf.data(), 4, n, f) == n;
+    if (ok) {
+        pdf.resize(n);
+        if (fread(pdf.data(), 4, n, f) != n) pdf.clear();     // no (complete) pdf block
+    }
+    fclose(f);
+    if (!ok) { g3d::set_error("vox2mesh: short read from %s", in_df); return G3D_ERR_IO; }
+    if (pdf.empty()) {                                         // main.cpp:180-192
+        pdf.assign(n, 0.f);
+        if (redcenter) {
+            const int c = dims[0] / 2, dim = dims[0], w = 1;
+            for (int i = c - w; i < c + w + 1; i++)
+                for (int j = c - w; j < c + w + 1; j++)
+                    for (int k = c - w; k < c + w + 1; k++) {
+                        const int64_t q = (int64_t)i * dim * dim + (int64_t)j * dim + k;
+                        if (q >= 0 && (size_t)q < n) pdf[(size_t)q] = 1;
+                    }
+        }
+    }
+    float vs[3] = { 1.f, 1.f, 1.f };                           // voxelsize; grid2world is row-major on disk
+    if (is_unitless)
+        for (int a = 0; a < 3; ++a) vs[a] = sqrtf(g2w[a] * g2w[a] + g2w[4 + a] * g2w[4 + a] + g2w[8 + a] * g2w[8 + a]);   // SE3.h:118-122
+    const float thr = trunc * res;
+    std::string rows, verts, faces;
+    size_t nvis = 0;
+    static const float bv[8][3] = { { -1, -1, 1 }, { 1, -1, 1 }, { 1, 1, 1 }, { -1, 1, 1 }, { -1, -1, -1 }, { 1, -1, -1 }, { 1, 1, -1 }, { -1, 1, -1 } };   // Box3D.h:9-19
+    static const int be[12][3] = { { 0, 1, 2 }, { 2, 3, 0 }, { 1, 5, 6 }, { 6, 2, 1 }, { 7, 6, 5 }, { 5, 4, 7 }, { 4, 0, 3 }, { 3, 7, 4 },
+                                   { 4, 5, 1 }, { 1, 0, 4 }, { 3, 2, 6 }, { 6, 7, 3 } };                                                                   // Box3D.h:41-59
+    const float r3[3] = { 0.45f * vs[0] * res, 0.45f * vs[1] * res, 0.45f * vs[2] * res };                                                                // main.cpp:72
+    char buf[160];
+    for (int k = 0; k < dims[2]; k++)
+        for (int j = 0; j < dims[1]; j++)
+            for (int i = 0; i < dims[0]; i++) {
+                const size_t q = (size_t)k * dims[1] * dims[0] + (size_t)j * dims[0] + i;
+                if (!(fabsf(sdf[q]) <= thr)) continue;         // main.cpp:44,92
+                float col[3];
+                jet_color(pdf[q], col);
+                const uint32_t ci[3] = { (uint32_t)(255.0f * col[0]), (uint32_t)(255.0f * col[1]), (uint32_t)(255.0f * col[2]) };
+                snprintf(buf, sizeof buf, "%d %d %d %u %u %u\n", i, j, k, ci[0], ci[1], ci[2]);
+                rows += buf;
+                if (write_ply) {
+                    float p[3];
+                    for (int a = 0; a < 3; ++a)                // (grid2world * (i, j, k, 1)).topRows(3), main.cpp:48
+                        p[a] = ((g2w[4 * a] * (float)i + g2w[4 * a + 1] * (float)j) + g2w[4 * a + 2] * (float)k) + g2w[4 * a + 3] * 1.0f;
+                    for (int c = 0; c < 8; ++c) {
+                        for (int a = 0; a < 3; ++a) put_float(verts, bv[c][a] * r3[a] + p[a]);
+                        snprintf(buf, sizeof buf, "%u %u %u \n", (uint32_t)(uint8_t)ci[0], (uint32_t)(uint8_t)ci[1], (uint32_t)(uint8_t)ci[2]);
+                        verts += buf;
+                    }
+                    for (int e = 0; e < 12; ++e) {
+                        snprintf(buf, sizeof buf, "3 %zu %zu %zu \n", nvis * 8 + be[e][0], nvis * 8 + be[e][1], nvis * 8 + be[e][2]);
+                        faces += buf;
+                    }
+                }
+                ++nvis;
+            }
+    FILE* o = fopen(txt.c_str(), "w");
+    if (!o) { g3d::set_error("failed to open %s", txt.c_str()); return G3D_ERR_IO; }
+    ok = fwrite(rows.data(), 1, rows.size(), o) == rows.size();
+    ok = (fclose(o) == 0) && ok;
+    if (ok && write_ply) {
+        o = fopen(out_ply, "w");
+        if (!o) { g3d::set_error("failed to open %s", out_ply); return G3D_ERR_IO; }
+        fprintf(o, "ply\nformat ascii 1.0\ncomment generated by tinyply 2.2\nelement vertex %zu\nproperty float x\nproperty float y\n"
+                   "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nelement face %zu\n"
+                   "property list uchar uint vertex_indices\nend_header\n", nvis * 8, nvis * 12);
+        ok = fwrite(verts.data(), 1, verts.size(), o) == verts.size() && fwrite(faces.data(), 1, faces.size(), o) == faces.size();
+        ok = (fclose(o) == 0) && ok;
+    }
+    if (!ok) { g3d::set_error("vox2mesh: short write"); return G3D_ERR_IO; }
+    return G3D_OK;
+}
+

@@ -43,6 +43,8 @@ namespace {
 
 typedef unsigned long long u64;
 
+constexpr uint32_t kTriMask = 0x7ffffffu;           // low 27 bits of a key's low word: closest_tri (all ones = none)
+
 struct TdfWs {
     float4*   tri;          // 4 x float4 per triangle: TriRec (g3d_ptd.cuh)
     int4*     box;          // i0|i1<<16, j0|j1<<16, k0|k1<<16, mesh
@@ -178,10 +180,12 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
     int m = mesh_of(tri_off, n_mesh, t);
     int64_t v0 = vert_off[m], nv = vert_off[m + 1] - v0;
     uint32_t ip = tris[3 * t], iq = tris[3 * t + 1], ir = tris[3 * t + 2];
-    if (ip >= nv || iq >= nv || ir >= nv) {
+    // closest_tri is the mesh-local index in 27 bits: triangles of one mesh beyond that cannot be represented
+    const bool too_many = t - tri_off[m] >= (int64_t)kTriMask;
+    if (too_many || ip >= nv || iq >= nv || ir >= nv) {
         // undefined behaviour in the reference (out-of-bounds read); flag the mesh
         // and neutralise the triangle: NaN vertices never win a `<` and an empty box
-        if (status) atomicOr(status + m, G3D_MESH_BAD_INDEX);
+        if (status) atomicOr(status + m, too_many ? G3D_MESH_TOO_MANY_TRIS : G3D_MESH_BAD_INDEX);
         float qnan = __int_as_float(0x7fc00000);
         tri_out[4 * t] = tri_out[4 * t + 1] = tri_out[4 * t + 2] = tri_out[4 * t + 3] = make_float4(qnan, qnan, qnan, qnan);
         box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
@@ -668,7 +672,6 @@ constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and r
 // (three rounds need a 196 KB shared-memory carve-out at 7 CTAs per SM and lose more L1 than they gain: 13.8 ms
 // against 12.5 with two and 13.0 with one)
 __host__ __device__ constexpr int sweep_rounds(int nt) { return nt <= 256 ? 2 : 1; }   // rounds of a level sharing one queue
-constexpr uint32_t kTriMask = 0x7ffffffu;           // low 27 bits of a key's low word: closest_tri (all ones = none)
 
 __device__ __forceinline__ void sweep_dir(int s, int& di, int& dj, int& dk)
 {
@@ -1068,8 +1071,11 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
     if (rc != G3D_OK) return rc;
     if (p.mode != G3D_MODE_FAITHFUL && p.mode != G3D_MODE_EXACT) { set_error("tdf: unknown mode %d", p.mode); return G3D_ERR_INVALID; }
-    if (total_tris >= ((int64_t)1 << 27) - 1) {      // closest_tri shares a 32-bit word with 5 bits of bookkeeping
-        set_error("at most 2^27 - 2 triangles per call, got %lld", (long long)total_tris);
+    // Per MESH the limit is 2^27 - 2 triangles (closest_tri shares a 32-bit word with 5 bits of bookkeeping; checked
+    // on the device, where the offsets live: G3D_MESH_TOO_MANY_TRIS). Per CALL the evaluation queues hold global
+    // triangle numbers in 32 bits.
+    if (total_tris >= ((int64_t)1 << 32) - 1) {
+        set_error("at most 2^32 - 2 triangles per call, got %lld", (long long)total_tris);
         return G3D_ERR_INVALID;
     }
     if (n_mesh == 0) return G3D_OK;

@@ -47,14 +47,21 @@ class DatasetLoad(torch.utils.data.Dataset):
     """dataset_loader.py:155-189 with the grids resident in HBM.
 
     Two ways to fill it:
-      * DatasetLoad(data_list, truncation, ...) reads the reference's files once (not per item
-        per epoch) using `params` (the dict of parameters.json) for the directories;
-      * DatasetLoad.from_tensors(...) wraps grids produced on the GPU by tdf_batch /
-        raycast_batch -- no files at all.
-    Use with DataLoader(num_workers=0): CUDA tensors must not cross a fork.
+      * DatasetLoad(data_list, truncation, n_max_samples, transform) -- the reference's constructor. The reference
+        re-reads four files (and parameters.json) per item per epoch; here every file is read ONCE, in the
+        constructor, in the process that builds the data set (`params`: the dict of parameters.json, default
+        "../parameters.json" exactly as dataset_loader.py:177 opens it). An item whose files cannot be read does not
+        poison the others: the exception is kept and raised when THAT item is asked for, as the reference would;
+      * DatasetLoad.from_tensors(...) wraps grids produced on the GPU by tdf_batch / raycast_batch -- no files.
+    Every item carries the reference's five keys ('name', 'occ_grid', 'occ_gt', 'occ_df_gt', 'df_gt').
+    The tensors are CUDA tensors, which must not cross a fork: use DataLoader(num_workers=0). The reference
+    trainers pass num_workers=2 (trainer_df.py:81); asking for an item from a worker process raises a RuntimeError
+    that says so instead of CUDA's "cannot re-initialize CUDA in forked subprocess".
     """
 
-    def __init__(self, data_list, truncation, n_max_samples=-1, transform=None, params=None, device=None):
+    KEYS = ("occ_grid", "occ_gt", "occ_df_gt", "df_gt")
+
+    def __init__(self, data_list, truncation, n_max_samples=-1, transform=None, params=None, device=None, _load=True):
         self.data_list = data_list
         self.n_samples = len(data_list)
         self.transform = transform
@@ -62,15 +69,25 @@ class DatasetLoad(torch.utils.data.Dataset):
         if n_max_samples != -1:
             self.n_samples = min(self.n_samples, n_max_samples)
         self._grids = None
+        self._errors = {}
         self._params = params
         self._device = device
+        if _load:
+            self._load_files()
 
     @classmethod
     def from_tensors(cls, names, occ_grid, occ_gt, df_gt, occ_df_gt=None, truncation=3.0):
-        """occ_grid/occ_gt/df_gt: f32 [N,D,H,W] CUDA tensors ([z][y][x])."""
-        self = cls([{"synset_id": "", "model_id": n} for n in names], truncation)
-        self._grids = {"occ_grid": occ_grid, "occ_gt": occ_gt, "df_gt": df_gt,
-                       "occ_df_gt": occ_df_gt if occ_df_gt is not None else None}
+        """occ_grid / occ_gt / df_gt: f32 [N,D,H,W] CUDA tensors ([z][y][x]). Without occ_df_gt the chamfer field of
+        occ_gt is computed on the GPU -- what occ_to_df.py:16-62 saves as *_occ_df.npy and load_occ_df
+        (dataset_loader.py:144-152) clamps at the truncation."""
+        self = cls([{"synset_id": "", "model_id": n} for n in names], truncation, _load=False)
+        if occ_df_gt is None:
+            from .data_utils import _batch
+            occ_df_gt = _batch(occ_gt.reshape(-1, *occ_gt.shape[-3:]), truncation, False, truncation)
+        self._grids = {"occ_grid": occ_grid, "occ_gt": occ_gt, "df_gt": df_gt, "occ_df_gt": occ_df_gt}
+        for k, g in self._grids.items():
+            if g.shape[0] != len(names):
+                raise ValueError("%s holds %d grids for %d names" % (k, g.shape[0], len(names)))
         return self
 
     def __len__(self):
@@ -82,25 +99,29 @@ class DatasetLoad(torch.utils.data.Dataset):
             with open("../parameters.json") as f:                 # dataset_loader.py:177
                 self._params = json.load(f)
         p = self._params
-        keys = ("occ_grid", "occ_gt", "df_gt", "occ_df_gt")
-        cols = {k: [] for k in keys}
-        for e in self.data_list[:self.n_samples]:
+        device = _device(self._device)
+        d = config.vox_dim
+        self._grids = {k: torch.zeros((self.n_samples, d, d, d), dtype=torch.float32, device=device) for k in self.KEYS}
+        for i, e in enumerate(self.data_list[:self.n_samples]):
             s, m = e["synset_id"], e["model_id"]
-            cols["occ_grid"].append(load_occ(p["shapenet_raytraced"] + s + "/" + m + ".txt", self._device))
-            cols["occ_gt"].append(load_occ(p["shapenet_voxelized"] + s + "/" + m + "__0__.txt", self._device))
-            cols["df_gt"].append(load_df(p["shapenet_voxelized"] + s + "/" + m + "__0__.df", self.truncation, self._device))
-            f = p["shapenet_voxelized"] + s + "/" + m + "_occ_df.npy"
-            cols["occ_df_gt"].append(load_occ_df(f, self.truncation, self._device) if os.path.exists(f) else None)
-        self._grids = {k: (torch.cat(v, 0) if all(x is not None for x in v) else None) for k, v in cols.items()}
+            vox = p["shapenet_voxelized"] + s + "/" + m
+            try:                                                  # the four loads of dataset_loader.py:179-187
+                self._grids["occ_grid"][i] = load_occ(p["shapenet_raytraced"] + s + "/" + m + ".txt", device)[0]
+                self._grids["occ_gt"][i] = load_occ(vox + "__0__.txt", device)[0]
+                self._grids["df_gt"][i] = load_df(vox + "__0__.df", self.truncation, device)[0]
+                self._grids["occ_df_gt"][i] = load_occ_df(vox + "_occ_df.npy", self.truncation, device)[0]
+            except Exception as err:                              # noqa: BLE001 -- raised again from __getitem__(i)
+                self._errors[i] = err
 
     def __getitem__(self, index):
         if index >= self.n_samples:
             raise IndexError(index)
-        if self._grids is None:
-            self._load_files()
-        g = self._grids
+        if torch.utils.data.get_worker_info() is not None:
+            raise RuntimeError("generate3d_b200.DatasetLoad keeps its grids in GPU memory and cannot be read from a "
+                               "DataLoader worker process: build the DataLoader with num_workers=0")
+        if index in self._errors:
+            raise self._errors[index]
         item = {"name": self.data_list[index]["model_id"]}
-        for k in ("occ_grid", "occ_gt", "occ_df_gt", "df_gt"):
-            if g.get(k) is not None:
-                item[k] = g[k][index].unsqueeze(0)                # [1,D,H,W]
+        for k in self.KEYS:
+            item[k] = self._grids[k][index].unsqueeze(0)          # [1,D,H,W]
         return item

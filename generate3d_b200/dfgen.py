@@ -108,8 +108,16 @@ def tdf_batch(verts, vert_off, tris, tri_off, dim=32, padding=0, is_unit_cube=1,
     """What `dfgen <obj> dim padding unit out.df` + vox2mesh + load_df + apply_log_transform
     produce for a whole batch of meshes, on the GPU: dict of [n_mesh, dim, dim, dim] tensors
     ([z][y][x], voxel units) / packed occupancy words."""
-    p, _ = dfgen_geometry(dim, padding, is_unit_cube,
-                          None if is_unit_cube else _bbox(verts)[0], None if is_unit_cube else _bbox(verts)[1])
+    if is_unit_cube:
+        p, _ = dfgen_geometry(dim, padding, 1)
+    else:
+        # dfgen derives the grid from the bounding box of ITS mesh (main.cpp:66-76): with several meshes in one call
+        # a common box would silently give every model a different field than its own dfgen run
+        if int(vert_off.shape[0]) - 1 > 1:
+            raise ValueError("is_unit_cube=0 places the grid on each mesh's own bounding box: call tdf_batch once per mesh "
+                             "(or pass explicit TdfParams to tdf_batch_params)")
+        bmin, bmax = _bbox(verts)
+        p, _ = dfgen_geometry(dim, padding, 0, bmin, bmax)
     p.trunc, p.occ_thresh, p.mode = float(trunc), float(occ_thresh), _MODES[mode]
     return tdf_batch_params(verts, vert_off, tris, tri_off, p, outputs, device, out)
 
@@ -163,6 +171,9 @@ def read_df(path):
     L = _lib.lib()
     dims = np.zeros(3, np.int32)
     _lib.check(L.g3d_read_df(os.fsencode(path), dims.ctypes.data, None, None, None, 0))
+    n = int(dims[0]) * int(dims[1]) * int(dims[2])
+    if min(int(d) for d in dims) < 0 or 80 + 4 * n > os.path.getsize(path):      # untrusted header: never allocate on its say-so
+        raise _lib.G3DError(-4, "read_df: %s: header dims %s do not fit the file" % (path, dims.tolist()))
     sdf = np.empty((int(dims[2]), int(dims[1]), int(dims[0])), np.float32)
     res = C.c_float()
     g = np.zeros(16, np.float32)
@@ -176,6 +187,13 @@ def occ_rows_gt(occ_zyx, color=(0, 169, 255)):
     a = occ_zyx.detach().cpu().numpy() if torch.is_tensor(occ_zyx) else np.asarray(occ_zyx)
     k, j, i = np.nonzero(a)
     return "".join("%d %d %d %d %d %d\n" % (x, y, z, *color) for x, y, z in zip(i, j, k))
+
+
+def vox2mesh(in_df, out_ply, is_unitless=False, redcenter=False, cmap="jet", trunc=1.0, write_ply=True):
+    """The vox2mesh executable as a function (vox2mesh/main.cpp:131-203): .df -> <out>.txt (GT occupancy rows) and,
+    unless write_ply is False, the cube-per-voxel ASCII PLY. Host only."""
+    _lib.check(_lib.lib().g3d_vox2mesh(os.fsencode(in_df), os.fsencode(out_ply), int(bool(is_unitless)), int(bool(redcenter)),
+                                       cmap.encode(), float(trunc), int(bool(write_ply))))
 
 
 def dfgen(mesh_path, dim, padding, is_unit_cube, out_path, mode="faithful", write_occ_txt=False):

@@ -48,6 +48,7 @@ extern "C" {
 #define G3D_MESH_OK             0
 #define G3D_MESH_BAD_INDEX      1   /* a face references a vertex >= n_vert (UB in the reference) */
 #define G3D_MESH_EMPTY          2   /* no vertices or no faces (LoaderMesh.h:83 asserts) */
+#define G3D_MESH_TOO_MANY_TRIS  4   /* more than 2^27 - 2 triangles in ONE mesh: the surplus is ignored */
 
 int         g3d_version(void);
 const char* g3d_last_error(void);
@@ -99,8 +100,10 @@ size_t g3d_tdf_workspace_bytes(int32_t n_mesh, int64_t total_verts, int64_t tota
  * tris      u32 [total_tris, 3]    vertex indices LOCAL to their mesh
  * tri_off   i64 [n_mesh + 1]       first triangle of each mesh
  * total_verts/total_tris repeat vert_off[n_mesh]/tri_off[n_mesh] so that the
- * host never has to read device memory. At most 2^27 - 2 triangles per call
- * (G3D_ERR_INVALID beyond; split the batch).
+ * host never has to read device memory. One MESH may hold at most 2^27 - 2 triangles
+ * (closest_tri shares a 32-bit word with 5 bits of sweep bookkeeping; a larger mesh is
+ * flagged G3D_MESH_TOO_MANY_TRIS and its surplus triangles are ignored); one CALL at
+ * most 2^32 - 2 in total (G3D_ERR_INVALID beyond; split the batch).
  */
 int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_verts,
                   const uint32_t* tris, const int64_t* tri_off, int64_t total_tris,
@@ -166,6 +169,11 @@ int g3d_raycast_batch_host(g3d_context* ctx, const uint8_t* depth, const float* 
                            int32_t clamp_max, int32_t dim, uint32_t* occ_bits, float* occ_f32,
                            int64_t* index_map);
 
+/* Page-locked host memory for the *_host entry points (pageable memory works but serialises the copies).
+ * NULL on failure (g3d_last_error has the reason). */
+void* g3d_host_alloc(size_t bytes);
+void  g3d_host_free(void* p);
+
 /* ------------------------------------------------------- dfgen driver ------
  * src/dfgen/main.cpp:45-114 without the mesh: fills params (ni..dx, out_scale
  * = dim) and the row-major grid2world of the .df header. bbox_* are only read
@@ -181,6 +189,18 @@ int g3d_write_df(const char* path, const int32_t* dims3, float res, const float*
                  const float* sdf);
 int g3d_read_df(const char* path, int32_t* dims3, float* res, float* grid2world16, float* sdf,
                 int64_t capacity);
+
+/* vox2mesh (src/vox2mesh/main.cpp:131-203), the second process CADVoxelization.py:33-37 spawns per model, as
+ * a function: reads a .df (LoaderVOX.h:20-46, optional trailing pdf block included), writes
+ *   <out with its extension replaced by .txt>  rows "i j k R G B" for every voxel with |sdf| <= trunc * res in
+ *                                             k, j, i loop order (main.cpp:86-104) -- the GT occupancy file
+ *                                             load_occ reads; colour = cmap(pdf), jet(0) = 0 169 255;
+ *   <out>                                      (when write_ply != 0) the ASCII PLY of one 0.9-voxel cube per such
+ *                                             voxel that tinyply writes there (main.cpp:37-84,106-129).
+ * Host-only: no GPU involved. cmap: "jet" (the default; NULL = "jet"); the other tables of Colormap.h are not
+ * carried (G3D_ERR_INVALID). is_unitless != 0 scales the cubes by the column norms of grid2world (main.cpp:172-178). */
+int g3d_vox2mesh(const char* in_df, const char* out_ply, int32_t is_unitless, int32_t redcenter, const char* cmap,
+                 float trunc, int32_t write_ply);
 
 /* ---------------------------------------------------- "next" rows ----
  * occ_to_df (Network/data_utils.py:115-168; occ_to_df.py:16-62): occupancy -> 26-neighbour chamfer

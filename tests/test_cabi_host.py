@@ -109,3 +109,73 @@ def test_load_mesh_obj_and_ply(g3d, tmp_path):
     assert np.array_equal(v3, v) and np.array_equal(t3, t)
     with pytest.raises(g3d.G3DError):
         dfgen.load_mesh(str(tmp_path / "m.stl"))
+
+
+def test_read_df_rejects_overflowing_headers(g3d, tmp_path):
+    """Header dims are untrusted: three large dims whose product wraps must not slip past the capacity check."""
+    from generate3d_b200 import dfgen
+    L = g3d.lib()
+    bad = tmp_path / "bad.df"
+    for dims in ([1 << 21, 1 << 21, 1 << 21], [70000, 1, 1], [-1, 4, 4], [65536, 65536, 65536]):
+        with open(bad, "wb") as f:
+            f.write(np.asarray(dims, np.int32).tobytes() + np.float32(1).tobytes() + np.zeros(16, np.float32).tobytes())
+            f.write(np.zeros(4096, np.float32).tobytes())
+        out = np.zeros(64, np.float32)
+        d3 = np.zeros(3, np.int32)
+        rc = L.g3d_read_df(os.fsencode(str(bad)), d3.ctypes.data, None, None, out.ctypes.data, 64)
+        assert rc == -1 and not out.any(), dims
+    with pytest.raises(g3d.G3DError):
+        dfgen.read_df(str(bad))
+
+
+def _vox2mesh_expected_arrays(sdf, g2w, res, trunc, unitless):
+    """numpy restatement of get_position_and_color_from_vox (vox2mesh/main.cpp:37-84) for pdf = 0 / jet."""
+    bv = np.float32([[-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1], [-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1]])
+    be = np.uint32([[0, 1, 2], [2, 3, 0], [1, 5, 6], [6, 2, 1], [7, 6, 5], [5, 4, 7], [4, 0, 3], [3, 7, 4], [4, 5, 1], [1, 0, 4],
+                    [3, 2, 6], [6, 7, 3]])
+    M = g2w.reshape(4, 4).astype(np.float32)
+    vs = np.sqrt((M[:3, :3] ** 2).sum(0, dtype=np.float32)).astype(np.float32) if unitless else np.ones(3, np.float32)
+    r3 = (np.float32(0.45) * vs * np.float32(res)).astype(np.float32)
+    k, j, i = np.nonzero(np.abs(sdf) <= np.float32(trunc) * np.float32(res))
+    P = np.stack([((M[a, 0] * i.astype(np.float32) + M[a, 1] * j.astype(np.float32)) + M[a, 2] * k.astype(np.float32)) + M[a, 3]
+                  for a in range(3)], 1).astype(np.float32)
+    V = (bv[None] * r3[None, None] + P[:, None]).astype(np.float32).reshape(-1, 3)
+    Cc = np.tile(np.uint8([0, 169, 255]), (len(V), 1))
+    F = (be[None] + (np.arange(len(P), dtype=np.uint32) * 8)[:, None, None]).reshape(-1, 3).astype(np.uint32)
+    return np.ascontiguousarray(V), np.ascontiguousarray(Cc), np.ascontiguousarray(F), (i, j, k)
+
+
+@pytest.mark.parametrize("unitless", [0, 1])
+def test_vox2mesh_txt_and_ply(g3d, oracle, tmp_path, unitless):
+    """g3d_vox2mesh / bin/vox2mesh: the .txt equals the oracle's restatement of write_txt (vox2mesh/main.cpp:86-104);
+    the PLY equals what the REFERENCE's tinyply writes (compiled in place) for the arrays main.cpp:37-84 builds."""
+    import subprocess
+    from generate3d_b200 import dfgen
+    v, t = S.table_mesh(3, 5)
+    g = oracle.dfgen(t, v, 32)
+    df = tmp_path / "m__0__.df"
+    oracle.write_df(str(df), g["sdf"], g["grid2world"])
+    ply = tmp_path / "m__0__.ply"
+    dfgen.vox2mesh(str(df), str(ply), is_unitless=bool(unitless))
+    assert (tmp_path / "m__0__.txt").read_text() == oracle.gt_occ_txt_rows(g["sdf"])
+    # the executable with the argv CADVoxelization.py:35 passes writes the same two files
+    exe = os.path.join(os.path.dirname(g3d.LIB_PATH), "bin", "vox2mesh")
+    ply2 = tmp_path / "cli.ply"
+    subprocess.check_call([exe, "--in", str(df), "--out", str(ply2), "--is_unitless", str(unitless)])
+    assert ply2.read_bytes() == ply.read_bytes()
+    assert (tmp_path / "cli.txt").read_text() == (tmp_path / "m__0__.txt").read_text()
+    assert subprocess.call([exe, "--in", str(df)], stderr=subprocess.DEVNULL) == 1          # --out is required
+    assert subprocess.call([exe, "--in=" + str(df), "--out=" + str(ply2), "--trunc=0.5"]) == 0
+    head = ply.read_bytes()[:400].decode()
+    assert head.startswith("ply\nformat ascii 1.0\ncomment generated by tinyply 2.2\nelement vertex ")
+    if oracle.ref_obj_available():
+        V, Cc, F, _ = _vox2mesh_expected_arrays(g["sdf"], g["grid2world"], 1.0, 1.0, unitless)
+        L = C.CDLL(os.path.join(os.path.dirname(oracle.__file__), "_ref", "libg3d_ref_obj.so"))
+        want = tmp_path / "ref.ply"
+        assert L.g3d_ref_write_ply(os.fsencode(str(want)), V.ctypes.data_as(C.c_void_p), C.c_int64(len(V)),
+                                   Cc.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), C.c_int64(len(F))) == 0
+        assert ply.read_bytes() == want.read_bytes()
+    with pytest.raises(g3d.G3DError):
+        dfgen.vox2mesh(str(df), str(tmp_path / "noext"))
+    with pytest.raises(g3d.G3DError):
+        dfgen.vox2mesh(str(df), str(ply), cmap="magma")

@@ -643,3 +643,140 @@ def test_two_streams_do_not_share_scratch(g3d):
     torch.cuda.synchronize()
     assert torch.equal(qa["sdf"], ra["sdf"]) and torch.equal(qa["closest_tri"], ra["closest_tri"])
     assert torch.equal(qb["sdf"], rb["sdf"]) and torch.equal(qb["closest_tri"], rb["closest_tri"])
+
+
+def _write_obj(path, v, t, fmt="%.9g"):
+    with open(path, "w") as f:
+        for p in v:
+            f.write(("v " + fmt + " " + fmt + " " + fmt + "\n") % tuple(p))
+        for tri in t:
+            f.write("f %d %d %d\n" % tuple(int(x) + 1 for x in tri))
+
+
+def test_dfgen_cli_batch_mode_equals_reference_program(g3d, oracle, tmp_path):
+    """`dfgen --batch list dim padding unit` (SURVEY 8b extension): one process and one CUDA context for a list of
+    models. Every .df is byte-identical to what the reference program writes for that model (oracle/_ref/dfgen_ref:
+    reference core + reference OBJ reader run as a program; the C port where _ref is absent), the .txt equals
+    vox2mesh's rows, an unreadable model is reported (exit code 4) without disturbing the others, and chunking does
+    not change a byte."""
+    cli = os.path.join(os.path.dirname(g3d.LIB_PATH), "bin", "dfgen")
+    ref_exe = os.path.join(os.path.dirname(oracle.__file__), "_ref", "dfgen_ref")
+    rows = []
+    for k in range(7):
+        v, t = S.table_mesh(2 + k % 4, 80 + k, scale=0.75 + 0.03 * k, rot_y=0.4 * k)
+        obj = tmp_path / ("m%d.obj" % k)
+        _write_obj(obj, v, t, "%.7f" if k % 2 else "%.9g")
+        rows.append((str(obj), str(tmp_path / ("m%d__0__.df" % k)), v, t))
+    broken = tmp_path / "broken.obj"
+    broken.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 0 1 2\n")
+    lst = tmp_path / "list.txt"
+    lst.write_text("".join("%s %s\n" % (r[0], r[1]) for r in rows[:4]) + "%s %s\n" % (broken, tmp_path / "broken.df") +
+                   "".join("%s %s\n" % (r[0], r[1]) for r in rows[4:]))
+    out = subprocess.run([cli, "--batch", str(lst), "32", "0", "1", "--occ-txt", "--chunk", "3"], capture_output=True, text=True)
+    assert out.returncode == 4 and "7 of 8 models written, 1 failed" in out.stdout, out.stdout[-500:] + out.stderr[-500:]
+    assert not (tmp_path / "broken.df").exists()
+    for objp, dfp, v, t in rows:
+        want = tmp_path / "want.df"
+        if os.path.exists(ref_exe):
+            subprocess.check_call([ref_exe, objp, "32", "0", "1", str(want)], stdout=subprocess.DEVNULL)
+        else:
+            v32, t32 = np.loadtxt(objp, usecols=(1, 2, 3), max_rows=len(v), dtype=np.float32), t
+            g = oracle.dfgen(t32, v32, 32)
+            oracle.write_df(str(want), g["sdf"], g["grid2world"])
+        assert open(dfp, "rb").read() == want.read_bytes(), objp
+        sdf = np.frombuffer(want.read_bytes()[80:], np.float32).reshape(32, 32, 32)
+        assert open(dfp[:-3] + ".txt").read() == oracle.gt_occ_txt_rows(sdf)
+    # one chunk for everything gives the same files; the single-model form too
+    lst2 = tmp_path / "list2.txt"
+    lst2.write_text("".join("%s %s\n" % (r[0], str(tmp_path / ("b%d.df" % k))) for k, r in enumerate(rows)))
+    assert subprocess.call([cli, "--batch", str(lst2), "32", "0", "1"], stdout=subprocess.DEVNULL) == 0
+    for k, r in enumerate(rows):
+        assert (tmp_path / ("b%d.df" % k)).read_bytes() == open(r[1], "rb").read()
+    single = tmp_path / "single.df"
+    subprocess.check_call([cli, rows[2][0], "32", "0", "1", str(single)], stdout=subprocess.DEVNULL)
+    assert single.read_bytes() == open(rows[2][1], "rb").read()
+    # is_unit_cube = 0: every model on its own bounding box (one submit per model), padding 1
+    lst3 = tmp_path / "list3.txt"
+    lst3.write_text("".join("%s %s\n" % (r[0], str(tmp_path / ("u%d.df" % k))) for k, r in enumerate(rows[:3])))
+    rc = subprocess.call([cli, "--batch", str(lst3), "32", "1", "0"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for k, r in enumerate(rows[:3]):
+        one = tmp_path / "one.df"
+        rc1 = subprocess.call([cli, r[0], "32", "1", "0", str(one)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if rc1 == 0:
+            assert (tmp_path / ("u%d.df" % k)).read_bytes() == one.read_bytes()
+    assert rc in (0, 4)
+
+
+def test_batch_of_more_than_2pow27_triangles_in_total(g3d, oracle):
+    """only the per-MESH triangle count is bounded by the 27-bit closest_tri field; a call may carry more
+    than 2^27 triangles in total. 1,060 copies of a 126,960-triangle table (134.6 M triangles, built on the device)
+    give 1,060 times the single-mesh field, which equals the oracle's."""
+    from generate3d_b200 import dfgen
+    v, t = S.table_mesh(46, 5)
+    copies = 1060
+    assert len(t) * copies > (1 << 27)
+    dv = torch.from_numpy(v).cuda().repeat(copies, 1)
+    dt = torch.from_numpy(t.view(np.int32)).cuda().repeat(copies, 1)
+    voff = torch.arange(copies + 1, dtype=torch.int64, device="cuda") * len(v)
+    toff = torch.arange(copies + 1, dtype=torch.int64, device="cuda") * len(t)
+    r = dfgen.tdf_batch(dv, voff, dt, toff, outputs=("sdf", "closest_tri", "status"))
+    torch.cuda.synchronize()
+    assert int(r["status"].abs().sum().item()) == 0
+    want = _oracle_full(oracle, v, t, 32)
+    assert np.array_equal(_bits(r["sdf"][0].cpu().numpy()), _bits(want["sdf"]))
+    assert np.array_equal(r["closest_tri"][copies - 1].cpu().numpy(), want["closest_tri"])
+    assert bool((r["sdf"] == r["sdf"][0:1]).all()) and bool((r["closest_tri"] == r["closest_tri"][0:1]).all())
+    del r, dv, dt
+    torch.cuda.empty_cache()
+
+
+def test_cadvoxelization_isolates_a_failing_batch_and_writes_ply(g3d, oracle, tmp_path, monkeypatch):
+    """a g3d_tdf_batch call that fails as a whole must not take the chunk down: the chunk is solved again
+    model by model and only the offender is reported. Also: write_ply=True leaves vox2mesh's .txt + .ply, and a
+    triangle budget splits heavy chunks without changing a byte."""
+    from generate3d_b200 import CADVoxelization as CV, dfgen, _lib
+    root = tmp_path / "shapenet"
+    want = {}
+    for k in range(5):
+        v, t = S.table_mesh(3, 160 + k, scale=0.9)
+        d = root / "04379243" / ("model%02d" % k) / "models"
+        d.mkdir(parents=True)
+        _write_obj(d / "model_normalized.obj", v, t)
+        want["model%02d" % k] = oracle.dfgen(t, v, 32)
+    models = CV.list_models({"shapenet": str(root)})
+    real = dfgen.tdf_batch
+    calls = []
+
+    def flaky(V, voff, T, toff, **kw):
+        n = len(voff) - 1
+        calls.append(n)
+        if n > 1:
+            raise _lib.G3DError(-2, "simulated device failure for a multi-model call")
+        if len(calls) == 4:                                         # the third single-model retry
+            raise _lib.G3DError(-1, "simulated bad model")
+        return real(V, voff, T, toff, **kw)
+    monkeypatch.setattr(dfgen, "tdf_batch", flaky)
+    out_root = str(tmp_path / "vox") + "/"
+    done, failed = CV.voxelize_models(models, out_root, chunk=8, write_ply=True)
+    assert calls[0] == 5 and calls[1:] == [1] * 5
+    assert done == 4 and len(failed) == 1 and "simulated bad model" in failed[0][1]
+    bad = failed[0][0]
+    for mid, g in want.items():
+        out = tmp_path / "vox" / "04379243" / (mid + "__0__.df")
+        if mid == bad:
+            assert not out.exists()
+            continue
+        ref = tmp_path / "ref.df"
+        oracle.write_df(str(ref), g["sdf"], g["grid2world"])
+        assert out.read_bytes() == ref.read_bytes()
+        assert (tmp_path / "vox" / "04379243" / (mid + "__0__.txt")).read_text() == oracle.gt_occ_txt_rows(g["sdf"])
+        assert (tmp_path / "vox" / "04379243" / (mid + "__0__.ply")).read_bytes().startswith(b"ply\nformat ascii 1.0\n")
+    monkeypatch.setattr(dfgen, "tdf_batch", real)
+    calls.clear()
+    done2, failed2 = CV.voxelize_models(models, str(tmp_path / "vox2") + "/", chunk=8, tri_budget=1100)   # 540 tris per model
+    assert done2 == 5 and not failed2
+    for mid in want:
+        a = (tmp_path / "vox2" / "04379243" / (mid + "__0__.df")).read_bytes()
+        ref = tmp_path / "ref.df"
+        oracle.write_df(str(ref), want[mid]["sdf"], want[mid]["grid2world"])
+        assert a == ref.read_bytes()
