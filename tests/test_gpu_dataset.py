@@ -37,7 +37,7 @@ def test_datasetload_constructor_path_equals_reference_items(g3d, golden_dir, tm
     assert len(ds) == 3
     for i, name in enumerate(names):
         item = ds[i]
-        assert sorted(item) == ["df_gt", "name", "occ_df_gt", "occ_gt", "occ_grid"] and item["name"] == name
+        assert set(item) == {"df_gt", "name", "occ_df_gt", "occ_gt", "occ_grid"} and item["name"] == name
         for k in ("occ_grid", "occ_gt", "occ_df_gt", "df_gt"):
             assert item[k].is_cuda and item[k].dtype == torch.float32 and tuple(item[k].shape) == (1, 32, 32, 32)
             assert np.array_equal(item[k].cpu().numpy().view(np.uint32), z[k][i].view(np.uint32)), (name, k)
