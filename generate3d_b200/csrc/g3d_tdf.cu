@@ -31,6 +31,7 @@
 // HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B; keys u64 per mesh in 4x4x4 bricks
 // (hi = phi bits, lo = sweep change code << 27 | closest_tri; see KeyMap); parity bits u32 [n_mesh, ceil(nvox/32)];
 // sweep order table (shared by all meshes).
+#include <cuda_fp16.h>
 #include <limits.h>
 #include <stdlib.h>
 
@@ -173,7 +174,8 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
                 const uint32_t* __restrict__ tris, const int64_t* __restrict__ tri_off,
                 int64_t t_first, int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
                 int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status,
-                float4* __restrict__ aabb_out, float4* __restrict__ fast_out)
+                float4* __restrict__ fast_out, uint4* __restrict__ tmp_out, uint32_t* __restrict__ cell_count,
+                uint32_t* __restrict__ dil)
 {
     int64_t t = t_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_tris) return;
@@ -188,23 +190,8 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
         if (status) atomicOr(status + m, too_many ? G3D_MESH_TOO_MANY_TRIS : G3D_MESH_BAD_INDEX);
         float qnan = __int_as_float(0x7fc00000);
         tri_out[4 * t] = tri_out[4 * t + 1] = tri_out[4 * t + 2] = tri_out[4 * t + 3] = make_float4(qnan, qnan, qnan, qnan);
-        box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
-        if (aabb_out) {                            // same slot computation as below
-            const int64_t tbase = tri_off[m];
-            const uint64_t T = (uint64_t)(tri_off[m + 1] - tbase), tl = (uint64_t)(t - tbase);
-            uint64_t A = 40503u % (T ? T : 1);
-            for (;; ++A) {
-                uint64_t x = A, y = T;
-                while (y) { uint64_t r = x % y; x = y; y = r; }
-                if (x == 1 || T <= 1) break;
-            }
-            const int64_t slot = tbase + (int64_t)((tl * A) % (T ? T : 1));
-            // an inverted infinite box: infinitely far from everything (fmaxf would turn a NaN box into
-            // distance 0), and still carrying a valid triangle index for the case of an infinite bound
-            const float inf = __int_as_float(0x7f800000);
-            aabb_out[2 * slot] = make_float4(inf, inf, inf, __uint_as_float((uint32_t)tl));
-            aabb_out[2 * slot + 1] = make_float4(-inf, -inf, -inf, 0.f);
-        }
+        if (box_out) box_out[t] = make_int4(1, 1, 1, m);        // lo=1 > hi=0 on every axis
+        if (tmp_out) tmp_out[t] = make_uint4(0u, 0u, 0u, exact::kNoCell);   // exact mode: not part of the cell index
         if (fast_out) for (int q = 0; q < 5; ++q) fast_out[5 * t + q] = make_float4(qnan, qnan, qnan, qnan);
         return;
     }
@@ -214,38 +201,6 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
     float xp[3] = { pp[0], pp[1], pp[2] }, xq[3] = { pq[0], pq[1], pq[2] }, xr[3] = { pr[0], pr[1], pr[2] };
     store_trirec(tri_out + 4 * t, make_trirec({ xp[0], xp[1], xp[2] }, { xq[0], xq[1], xq[2] }, { xr[0], xr[1], xr[2] }));
     if (fast_out) exact::store_fastrec(fast_out + 5 * t, { xp[0], xp[1], xp[2] }, { xq[0], xq[1], xq[2] }, { xr[0], xr[1], xr[2] });
-    if (aabb_out) {
-        // exact mode: world-space bounding box of the triangle, stored at a pseudo-random position of the
-        // mesh's box array (p = tl * A mod T, A coprime with T) with the triangle's own index in lo.w.
-        // Streaming the boxes in that order makes every tile a uniform sample of the mesh, so a voxel's
-        // running minimum drops to its final value after a few tiles instead of creeping towards it along
-        // a face; fewer pairs survive the cull and far fewer set a new minimum. Ties are still broken by
-        // the ORIGINAL index, so the result does not depend on the order.
-        const int64_t tbase = tri_off[m];
-        const uint64_t T = (uint64_t)(tri_off[m + 1] - tbase), tl = (uint64_t)(t - tbase);
-        uint64_t A = 40503u % (T ? T : 1);
-        for (;; ++A) {
-            uint64_t x = A, y = T;
-            while (y) { uint64_t r = x % y; x = y; y = r; }
-            if (x == 1 || T <= 1) break;
-        }
-        const int64_t slot = tbase + (int64_t)((tl * A) % (T ? T : 1));
-        float4 lo = make_float4(fminf(xp[0], fminf(xq[0], xr[0])), fminf(xp[1], fminf(xq[1], xr[1])),
-                                fminf(xp[2], fminf(xq[2], xr[2])), __uint_as_float((uint32_t)tl));
-        float4 hi = make_float4(fmaxf(xp[0], fmaxf(xq[0], xr[0])), fmaxf(xp[1], fmaxf(xq[1], xr[1])),
-                                fmaxf(xp[2], fmaxf(xq[2], xr[2])), 0.f);
-        // a non-finite vertex gives NaN distances, which never win in the reference: push the box
-        // infinitely far away (fminf/fmaxf would silently drop the NaNs and keep a finite box)
-        float chk = xp[0] + xp[1] + xp[2] + xq[0] + xq[1] + xq[2] + xr[0] + xr[1] + xr[2];
-        if (!(fabsf(chk) < 3.0e38f)) {
-            const float inf = __int_as_float(0x7f800000);
-            lo.x = lo.y = lo.z = inf;
-            hi.x = hi.y = hi.z = -inf;
-        }
-        aabb_out[2 * slot] = lo;
-        aabb_out[2 * slot + 1] = hi;
-    }
-
     const int dims[3] = { P.ni, P.nj, P.nk };
     double fp[3], fq[3], fr[3];
     int lo[3], hi[3];
@@ -261,7 +216,14 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
         lo[a] = (int)(l < 0 ? 0 : (l > dims[a] - 1 ? dims[a] - 1 : l));
         hi[a] = (int)(u < 0 ? 0 : (u > dims[a] - 1 ? dims[a] - 1 : u));
     }
-    box_out[t] = make_int4(lo[0] | (hi[0] << 16), lo[1] | (hi[1] << 16), lo[2] | (hi[2] << 16), m);
+    if (box_out) box_out[t] = make_int4(lo[0] | (hi[0] << 16), lo[1] | (hi[1] << 16), lo[2] | (hi[2] << 16), m);
+    if (tmp_out) {
+        // exact mode: the triangle joins the mesh's cell index. A non-finite vertex gives NaN distances, which never
+        // win in the reference: such a triangle is left out altogether.
+        const float chk = xp[0] + xp[1] + xp[2] + xq[0] + xq[1] + xq[2] + xr[0] + xr[1] + xr[2];
+        if (fabsf(chk) < 3.0e38f) exact::index_triangle(fp, fq, fr, m, t, P, tmp_out, cell_count, dil);
+        else tmp_out[t] = make_uint4(0u, 0u, 0u, exact::kNoCell);
+    }
 
     // cpp:147-160: x-ray intersection parity
     int j0 = clampi(x86_d2i(ceil(dmin(fp[1], dmin(fq[1], fr[1])))), 0, P.nj - 1);
@@ -1095,6 +1057,9 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     if (p.mode == G3D_MODE_EXACT) {
         exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
         key = w.key; parity = w.parity;
+        G3D_CUDA_TRY(cudaMemsetAsync(w.cursor, 0, (size_t)n_mesh * (exact::ncell_of(p) + 1) * 4, stream));
+        G3D_CUDA_TRY(cudaMemsetAsync(w.dil, 0, (size_t)n_mesh * 4, stream));
+        G3D_CUDA_TRY(cudaMemsetAsync(w.occ, 0, (size_t)n_mesh * ((exact::ncell_of(p) + 31) / 32) * 4, stream));
     } else {
         TdfWs w = carve(ws, n_mesh, total_tris, p);
         key = w.key; parity = w.parity;
@@ -1118,12 +1083,12 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* 
     if (p.mode == G3D_MODE_EXACT) {
         exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
         tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, w.aabb, w.fast);
+            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, nullptr, w.parity, out.status, w.fast, w.tmp, w.cursor, w.dil);
         prof_mark(ST_PREP, stream);
     } else {
         TdfWs w = carve(ws, n_mesh, total_tris, p);
         tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr);
+            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr);
         prof_mark(ST_PREP, stream);
         // [t0, t1) are the triangles of meshes [m0, m1). Batches of small grids: one CTA per 16^3 block of a mesh, keys in
         // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel, and so do
@@ -1152,35 +1117,35 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
     if (p.mode == G3D_MODE_EXACT) {
         exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
         if (total_tris > 0) {
-            constexpr int WX = exact::kWX, WY = exact::kWY, WZ = exact::kWZ, NT = WX * WY * WZ * 32, TILE = exact::kTile;
-            const int nbx = (p.ni + WX * 4 - 1) / (WX * 4), nby = (p.nj + WY * 4 - 1) / (WY * 4), nbz = (p.nk + WZ * 2 - 1) / (WZ * 2);
-            const int64_t nblocks = (int64_t)n_mesh * nbx * nby * nbz;
-            if (nblocks >= (int64_t)INT_MAX) { set_error("exact: too many blocks in one call (%lld)", (long long)nblocks); return G3D_ERR_INVALID; }
+            const int64_t ncell = exact::ncell_of(p), n_groups = (int64_t)n_mesh * ncell;
             const float far = (float)(p.ni + p.nj + p.nk) * p.dx;
             // distances up to R matter: trunc is in output units (phi * out_scale)
             float R = __builtin_inff();
             if (p.trunc < 3.0e38f && p.out_scale > 0.f) R = p.trunc / p.out_scale * 1.0001f;
-            static int strict = -1;                 // G3D_EXACT_STRICT=1: single-stage kernel (every pair evaluated faithfully)
-            if (strict < 0) { const char* e = getenv("G3D_EXACT_STRICT"); strict = (e && atoi(e)) ? 1 : 0; }
-            if (strict) {
-                const size_t smem = (size_t)2 * TILE * 32 + (size_t)TILE * 4 + 2 * 8 + 2 * 4;
-                G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                exact::tdf_exact_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
-                    w.tri, w.aabb, tri_off, w.parity, w.key, p, R, far, nbx, nby, nbz, cnt);
-            } else {
-                // filter margins of the two-stage kernel, scaled by the extent of the coordinates involved
-                float S = 0.f;
-                const int dims[3] = { p.ni, p.nj, p.nk };
-                for (int a = 0; a < 3; ++a) {
-                    S = fmaxf(S, fabsf(p.origin[a]));
-                    S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
-                }
-                const float eta = 0.f, kappa = 1e-10f * S * S;
-                const size_t smem = (size_t)3 * TILE * 32 + (size_t)2 * TILE * 4 + 3 * 8 + 4 * 4 + (size_t)(NT / 32) * 4 + (size_t)(NT / 32) * 64 * 4;
-                G3D_CUDA_TRY(cudaFuncSetAttribute(exact::tdf_exact2_kernel<WX, WY, WZ, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                exact::tdf_exact2_kernel<WX, WY, WZ, TILE><<<(unsigned)nblocks, NT, smem, stream>>>(
-                    w.tri, w.fast, w.aabb, tri_off, w.parity, w.key, p, R, far, eta, kappa, nbx, nby, nbz, cnt);
+            // filter margin of the two-stage evaluation, scaled by the extent of the coordinates involved
+            float S = 0.f;
+            const int dims[3] = { p.ni, p.nj, p.nk };
+            for (int a = 0; a < 3; ++a) {
+                S = fmaxf(S, fabsf(p.origin[a]));
+                S = fmaxf(S, fabsf(p.origin[a] + (float)dims[a] * p.dx));
             }
+            const float kappa = 1e-10f * S * S;
+            // the cell index: CSR starts, entries in cell order, cell boxes
+            exact::exact_scan_kernel<<<(unsigned)n_mesh, 256, 0, stream>>>(w.cursor, w.cell_start, ncell);
+            exact::exact_fill_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
+                w.tmp, tri_off, total_tris, n_mesh, ncell, w.cell_start, w.cursor, w.ent);
+            exact::exact_cellbox_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, stream>>>(
+                w.ent, tri_off, w.cell_start, ncell, n_groups, w.cellbox, w.occ);
+            prof_mark(ST_ORDER, stream);
+            const int64_t want = (n_groups + exact::kExactWarps - 1) / exact::kExactWarps;
+            const int64_t cap = (int64_t)sm_count() * 64;        // persistent warps: 16 CTAs per SM, 4 rounds of slack
+            const char* e_occ = getenv("G3D_EXACT_OCC");        // tuning override: resident CTAs per SM the kernel is compiled for
+            const int occv = e_occ ? atoi(e_occ) : 5;
+            const unsigned nb = (unsigned)(want < cap ? want : cap);
+#define G3D_EXACT_LAUNCH(MINB) exact::tdf_exact3_kernel<MINB><<<nb, exact::kExactWarps * 32, 0, stream>>>( \
+                w.tri, w.fast, w.ent, w.cell_start, w.cellbox, w.occ, w.dil, tri_off, w.parity, w.key, p, R, far, kappa, n_groups, cnt)
+            if (occv >= 8) G3D_EXACT_LAUNCH(8); else if (occv >= 6) G3D_EXACT_LAUNCH(6); else if (occv <= 3) G3D_EXACT_LAUNCH(3); else G3D_EXACT_LAUNCH(5);
+#undef G3D_EXACT_LAUNCH
             prof_mark(ST_EXACT, stream);
         }
     } else {

@@ -1,4 +1,4 @@
-// g3d_tdf_exact.cuh -- "exact" mode: brute-force nearest triangle with truncation culling.
+// g3d_tdf_exact.cuh -- "exact" mode: nearest triangle per voxel through a per-mesh cell grid.
 // Included by g3d_tdf.cu (shares tdf_prep / tdf_finalize and the key format).
 //
 // The reference's far field is only approximate (makelevelset3.h:7-11: beyond the 1-cell band a
@@ -11,224 +11,42 @@
 //     value (ni+nj+nk)*dx otherwise;
 //   * inside voxels (odd parity): always exact (the negative side is never clamped).
 //
-// One CTA owns an 8x8x8 block of voxels of one mesh (16 warps x a 4x4x2 brick, one voxel per lane)
-// and streams the mesh's triangle bounding boxes through shared memory in tiles, double-buffered
-// with 1-D TMA bulk copies (cp.async.bulk + mbarrier): while the warps work on tile i, tile i+1 is
-// in flight.
-//   phase A  all threads: tile boxes vs the block's box with the block's static radius -> compacted
-//            survivor list in shared memory;
-//   phase B  each warp: survivors vs its brick's box with the brick's RUNNING bound (the largest
-//            current best distance among its 32 voxels, a warp-shuffle max-reduce), 32 at a time
-//            via ballot; every survivor is then evaluated by all 32 lanes (the triangle record is a
-//            broadcast load) with the reference's distance function and merged with
-//            (d, t) < (best, best_t) lexicographic order = "lowest triangle index wins ties".
+// Spatial index (built per call, in voxel-index space, no host involvement):
+//   tdf_prep      per triangle: bounding box in grid coordinates, rounded OUTWARD to half precision; home cell =
+//                 the 2x2x2-node cell holding the box centre. A triangle whose box stays within its home cell
+//                 dilated by kSmallMax voxels is "small" and is counted into that cell; anything bigger goes to
+//                 the mesh's "large" list. The largest overhang of a small triangle is kept per mesh (dil).
+//   exact_scan    per mesh: exclusive scan of the cell counts -> CSR starts (the large list is pseudo-cell ncell)
+//   exact_fill    per triangle: entry {box (6 halves), mesh-local triangle index} to its CSR slot (16 B)
+//   exact_cellbox per cell: union of its entries' boxes (16 B: what a group tests before touching the list)
+//   tdf_exact3    one WARP per cell = per 2x2x2 group of voxels (lane = voxel x 4 triangle slots). The warp first
+//                 scans the large list, then its own cell, then the surrounding cells shell by shell (Chebyshev
+//                 rings of cells), inside a ring nearest cell box first, and stops at the first ring that cannot
+//                 reach below the group's running bound. Because the nearest cells come first the bound is tight
+//                 after the first few triangles, so a voxel meets a few dozen candidates instead of thousands.
+//   Per list, 32 entries at a time: entry box vs the group's box with the running bound -> survivors (ballot) ->
+//   four survivors at a time are rated against the 8 voxels (stage 1, cheap FMA squared distance with an error
+//   interval, no division or square root) -> the few pairs whose interval reaches below the voxel's running upper
+//   bound are queued and re-evaluated 32 at a time with the bit-faithful function (stage 2), which alone decides
+//   the result; a warp-shuffle min-reduce shares the running bounds between the four slots of a voxel and the
+//   eight voxels of the group.
 #pragma once
+// (needs <cuda_fp16.h>, included by g3d_tdf.cu at global scope: this file is included inside namespace g3d)
 
 namespace exact {
 
-// block shape in warps (each warp = a 4x4x2 brick) and triangle-box tile size. Small blocks and small tiles win:
-// a block barrier costs the slowest brick's time (a brick next to the surface rates thousands of pairs, a far one
-// none), and occupancy is bounded by the tile stages in shared memory. Measured on B200, 1,024 meshes, two-stage
-// kernel: 2x2x4 warps / 1024 boxes 105 ms; 2x1x2 / 512 (two barriers per tile) 67.7; one barrier per tile with
-// three stages: 2x1x2 / 512 90.4, / 256 56.4, / 128 67.1; 2x2x2 / 256 58.9; prefetching the next survivor's
-// record costs more than it hides (60.2 vs 56.4).
-constexpr int kWX = 2, kWY = 1, kWZ = 2;
-constexpr int kTile = 256;
-constexpr bool kPrefetchNext = false;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
+constexpr int kCell = 2;                  // nodes per cell and axis (one warp-group of 2x2x2 voxels per cell)
+constexpr float kSmallMax = 2.0f;         // overhang (voxels) beyond the home cell up to which a triangle is "small"
+constexpr uint32_t kNoCell = 0xffffffffu;
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// squared distance between two axis-aligned boxes (0 when they overlap); FMA is fine here, the
-// result only feeds a conservative comparison
-__device__ __forceinline__ float box_gap2(float4 alo, float4 ahi, V3 blo, V3 bhi)
-{
-    float gx = fmaxf(0.f, fmaxf(alo.x - bhi.x, blo.x - ahi.x));
-    float gy = fmaxf(0.f, fmaxf(alo.y - bhi.y, blo.y - ahi.y));
-    float gz = fmaxf(0.f, fmaxf(alo.z - bhi.z, blo.z - ahi.z));
-    return fmaf(gx, gx, fmaf(gy, gy, gz * gz));
-}
-
-// neutralised triangles carry an inverted infinite box (gap = inf): culled unless the bound is infinite,
-// in which case their NaN distances simply never win
-__device__ __forceinline__ float bound2_of(float r) { return fmaf(r * r, 1.001f, 1e-12f); }
-
-template <int WX, int WY, int WZ, int TILE>
-__global__ void __launch_bounds__(WX * WY * WZ * 32)
-tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb,
-                 const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
-                 g3d_tdf_params P, float R, float far, int nbx, int nby, int nbz, u64* counter)
-{
-    constexpr int NT = WX * WY * WZ * 32;
-    constexpr int BX = WX * 4, BY = WY * 4, BZ = WZ * 2;                      // nodes per block and axis
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [2][TILE * 2]
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 2 * TILE * 32);    // [TILE]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_list + TILE);             // [2]
-    int* s_count = reinterpret_cast<int*>(s_bar + 2);                         // [2]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nblk = nbx * nby * nbz;
-    const int mesh = blockIdx.x / nblk;
-    int b = blockIdx.x - mesh * nblk;
-    const int cbx = b % nbx; b /= nbx;
-    const int cby = b % nby, cbz = b / nby;
-    const int ni = P.ni, nj = P.nj, nk = P.nk;
-    const int64_t nvox = nvox_of(P);
-
-    // block = BX x BY x BZ nodes; warp -> 4x4x2 brick; lane -> node
-    const int bi0 = cbx * BX + (warp % WX) * 4, bj0 = cby * BY + ((warp / WX) % WY) * 4, bk0 = cbz * BZ + (warp / (WX * WY)) * 2;
-    const int i = bi0 + (lane & 3), j = bj0 + ((lane >> 2) & 3), k = bk0 + (lane >> 4);
-    const bool valid = i < ni && j < nj && k < nk;
-    bool inside = false;
-    if (valid) {                                    // running parity along i (makelevelset3.cpp:174-182)
-        const uint32_t* par = parity + (int64_t)mesh * ((nvox + 31) / 32);
-        int64_t r0 = (int64_t)ni * (j + (int64_t)nj * k), r1 = r0 + i;
-        int cnt = 0;
-        for (int64_t w = r0 >> 5; w <= (r1 >> 5); ++w) {
-            uint32_t m = par[w];
-            if (w == (r0 >> 5)) m &= 0xffffffffu << (r0 & 31);
-            if (w == (r1 >> 5)) m &= 0xffffffffu >> (31 - (r1 & 31));
-            cnt += __popc(m);
-        }
-        inside = cnt & 1;
-    }
-    const V3 gx = node_pos(i, j, k, P);
-    // like the reference's phi, the running minimum starts at `far` (makelevelset3.cpp:123): a triangle farther
-    // away than that never registers. Outside voxels may stop at the truncation radius instead.
-    float best = valid ? (inside ? far : fminf(R, far)) : 0.f;
-    uint32_t best_t = 0xffffffffu;
-
-    // boxes of the brick and of the block (node positions are monotone in the index)
-    const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
-    const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
-    const V3 blk_lo = node_pos(cbx * BX, cby * BY, cbz * BZ, P);
-    const V3 blk_hi = node_pos(min(cbx * BX + BX - 1, ni - 1), min(cby * BY + BY - 1, nj - 1), min(cbz * BZ + BZ - 1, nk - 1), P);
-    const int any_inside = __syncthreads_or(inside ? 1 : 0);
-    const float blk_bound2 = bound2_of(any_inside ? far : fminf(R, far));
-
-    const int64_t t0 = tri_off[mesh];
-    const int T = (int)(tri_off[mesh + 1] - t0);
-    const float4* Tm = tri + 4 * t0;
-    const float4* Bm = aabb + 2 * t0;
-    const int ntile = (T + TILE - 1) / TILE;
-    u64 n_pairs = 0, n_tests = 0;
-
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-        s_count[0] = s_count[1] = 0;
-    }
-    __syncthreads();
-    if (tid == 0 && ntile > 0) {
-        uint32_t bytes = (uint32_t)min(TILE, T) * 32u;
-        mbar_expect_tx(&s_bar[0], bytes);
-        bulk_g2s(s_box, Bm, bytes, &s_bar[0]);
-    }
-    for (int it = 0; it < ntile; ++it) {
-        const int st = it & 1;
-        const int tile_base = it * TILE;
-        const int tn = min(TILE, T - tile_base);
-        if (tid == 0 && it + 1 < ntile) {           // stage st^1 was released by the barrier ending iteration it-1
-            uint32_t bytes = (uint32_t)min(TILE, T - (tile_base + TILE)) * 32u;
-            mbar_expect_tx(&s_bar[st ^ 1], bytes);
-            bulk_g2s(s_box + (st ^ 1) * TILE * 2, Bm + 2 * (int64_t)(tile_base + TILE), bytes, &s_bar[st ^ 1]);
-        }
-        mbar_wait(&s_bar[st], (it >> 1) & 1);
-        const float4* box = s_box + st * TILE * 2;
-
-        // ---- phase A: block-level cull, compacted with one shared atomic per warp
-        for (int q0 = warp * 32; q0 < tn; q0 += NT) {
-            int q = q0 + lane;
-            bool pass = false;
-            if (q < tn) {
-                pass = box_gap2(box[2 * q], box[2 * q + 1], blk_lo, blk_hi) <= blk_bound2;
-                ++n_tests;
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_count[st], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)q;
-            }
-        }
-        __syncthreads();
-        const int nlist = s_count[st];
-        if (tid == 0) s_count[st ^ 1] = 0;          // nobody touches the other counter until the next iteration
-
-        // ---- phase B: brick-level cull with the running bound, then the distance evaluations
-        for (int l0 = 0; l0 < nlist; l0 += 32) {
-            float bound = best;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, d));
-            const float bound2 = bound2_of(bound);
-            uint32_t tq = 0;                         // the triangle's own index rides in lo.w of its box
-            bool pass = false;
-            if (l0 + lane < nlist) {
-                const int q = (int)s_list[l0 + lane];
-                const float4 lo = box[2 * q];
-                tq = __float_as_uint(lo.w);
-                pass = box_gap2(lo, box[2 * q + 1], brick_lo, brick_hi) <= bound2;
-                ++n_tests;
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, pass);
-            while (m) {
-                int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t t = __shfl_sync(0xffffffffu, tq, src);
-                const float d = point_triangle_distance(gx, load_trirec(Tm + 4 * (int64_t)t));
-                if (d < best || (d == best && best_t != 0xffffffffu && t < best_t)) { best = d; best_t = t; }
-                n_pairs += valid ? 1 : 0;
-            }
-        }
-        __syncthreads();                            // stage st and the list are free again
-    }
-    if (valid) {
-        float phi = (best_t == 0xffffffffu) ? far : best;
-        key[(int64_t)mesh * nvox + (i + (int64_t)ni * (j + (int64_t)nj * k))] = ((u64)__float_as_uint(phi) << 32) | best_t;
-    }
-    if (counter) {
-        if (n_pairs) atomicAdd(counter + 2, n_pairs);
-        if (n_tests) atomicAdd(counter + 3, n_tests);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// v2: two-stage evaluation. Stage 1 rates every surviving (voxel, triangle) pair with a cheap
-// squared distance that is free to use FMA (55 arithmetic instructions, no division, no square
-// root: the three clamped edge parameters use precomputed reciprocals and the saturate modifier).
-// Only pairs whose cheap distance is within a generous margin of the voxel's running cheap minimum
-// can be the minimum of the reference's float function; those few are queued and re-evaluated 32
-// at a time with the bit-faithful function (stage 2), which alone decides the result.
+// Two-stage evaluation. Stage 1 rates a (voxel, triangle) pair with a cheap squared distance that is free to use
+// FMA (55 arithmetic instructions, no division, no square root: the three clamped edge parameters use precomputed
+// reciprocals and the saturate modifier). Only pairs whose cheap distance is within a generous margin of the
+// voxel's running cheap minimum can be the minimum of the reference's float function; those few are queued and
+// re-evaluated 32 at a time with the bit-faithful function (stage 2), which alone decides the result.
 //
 // Why this is still exact: stage 1 works on intervals. For every non-flagged triangle the cheap squared
 // distance a2 comes with an error bound e2 = 2e-6 * (|x0-x3|^2 + the three squared edge lengths): every
@@ -242,7 +60,8 @@ tdf_exact_kernel(const float4* __restrict__ tri, const float4* __restrict__ aabb
 // <= d(t)(1+2e-6) for every t, hence a2(t0) - e2(t0) <= d(t0)^2 <= 1.00001 * ub2. kappa (1e-10 * S^2, S the
 // extent of the coordinates) covers distances so small that f's absolute rounding dominates. Triangles for which
 // no such bound holds -- slivers, zero-length edges, non-finite vertices -- are flagged at record-build time and
-// always go to stage 2.
+// always go to stage 2. The box culls in front of stage 1 compare a LOWER bound of d^2 (distance between the
+// outward-rounded boxes) with 1.001 * the largest lim2 of the group, so they never drop a possible minimiser.
 struct FastRec {                                     // 5 x float4 = 80 B
     float4 f0;   // x3.xyz, invdet (NaN = always evaluate faithfully)
     float4 f1;   // x13.xyz, m13
@@ -303,226 +122,535 @@ __device__ __forceinline__ float fast_dist2(V3 x0, const float4* __restrict__ p,
     return fmaxf(inside ? plane : edge, 0.f);
 }
 
-template <int WX, int WY, int WZ, int TILE>
-__global__ void __launch_bounds__(WX * WY * WZ * 32)
-tdf_exact2_kernel(const float4* __restrict__ tri, const float4* __restrict__ fast, const float4* __restrict__ aabb,
-                  const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity, u64* __restrict__ key,
-                  g3d_tdf_params P, float R, float far, float eta, float kappa, int nbx, int nby, int nbz, u64* counter)
+// ---------------------------------------------------------------------------------------------
+// boxes in voxel-index space, six halves in three words: (lo.x, lo.y) (lo.z, hi.x) (hi.y, hi.z)
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b)
 {
-    constexpr int NT = WX * WY * WZ * 32, NW = NT / 32;
-    constexpr int BX = WX * 4, BY = WY * 4, BZ = WZ * 2;                      // nodes per block and axis
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    float4* s_box = reinterpret_cast<float4*>(s_raw);                         // [3][TILE * 2]  TMA stages
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_raw + 3 * TILE * 32);    // [2][TILE]      block-level survivors
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_list + 2 * TILE);         // [3]
-    int* s_count = reinterpret_cast<int*>(s_bar + 3);                         // [3] (+1 pad)
-    float* s_wb = reinterpret_cast<float*>(s_count + 4);                      // [NW] running bound^2 of each brick
-    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_wb + NW);               // [NW][64]  t << 5 | owner lane
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t* q = s_queue + warp * 64;
-    const int nblk = nbx * nby * nbz;
-    const int mesh = blockIdx.x / nblk;
-    int b = blockIdx.x - mesh * nblk;
-    const int cbx = b % nbx; b /= nbx;
-    const int cby = b % nby, cbz = b / nby;
-    const int ni = P.ni, nj = P.nj, nk = P.nk;
-    const int64_t nvox = nvox_of(P);
-
-    const int bi0 = cbx * BX + (warp % WX) * 4, bj0 = cby * BY + ((warp / WX) % WY) * 4, bk0 = cbz * BZ + (warp / (WX * WY)) * 2;
-    const int i = bi0 + (lane & 3), j = bj0 + ((lane >> 2) & 3), k = bk0 + (lane >> 4);
-    const bool valid = i < ni && j < nj && k < nk;
-    bool inside = false;
-    if (valid) {                                    // running parity along i (makelevelset3.cpp:174-182)
-        const uint32_t* par = parity + (int64_t)mesh * ((nvox + 31) / 32);
-        int64_t r0 = (int64_t)ni * (j + (int64_t)nj * k), r1 = r0 + i;
-        int cnt = 0;
-        for (int64_t w = r0 >> 5; w <= (r1 >> 5); ++w) {
-            uint32_t m = par[w];
-            if (w == (r0 >> 5)) m &= 0xffffffffu << (r0 & 31);
-            if (w == (r1 >> 5)) m &= 0xffffffffu >> (31 - (r1 & 31));
-            cnt += __popc(m);
-        }
-        inside = cnt & 1;
-    }
-    const float INF = __int_as_float(0x7f800000);
-    const V3 gx = node_pos(i, j, k, P);
-    // stage-2 state (decides the result) and stage-1 state (decides who gets a stage-2 evaluation)
-    // like the reference's phi, the running minimum starts at `far` (makelevelset3.cpp:123): a triangle farther
-    // away than that never registers. Outside voxels may stop at the truncation radius instead.
-    const float start = inside ? far : fminf(R, far);
-    float best = valid ? start : 0.f;
-    uint32_t best_t = 0xffffffffu;
-    // pass to stage 2 iff a2 - e2 <= lim2 = 1.002 * ub2 + kappa, ub2 = smallest a2 + e2 seen (start^2 at first)
-    float ub2 = valid ? start * start : -1.f;
-    float lim2 = valid ? fmaf(ub2, 1.002f, kappa) : -1.f;
-    (void)eta; (void)INF;
-
-    const V3 brick_lo = node_pos(bi0, bj0, bk0, P);
-    const V3 brick_hi = node_pos(min(bi0 + 3, ni - 1), min(bj0 + 3, nj - 1), min(bk0 + 1, nk - 1), P);
-    const V3 blk_lo = node_pos(cbx * BX, cby * BY, cbz * BZ, P);
-    const V3 blk_hi = node_pos(min(cbx * BX + BX - 1, ni - 1), min(cby * BY + BY - 1, nj - 1), min(cbz * BZ + BZ - 1, nk - 1), P);
-
-    auto warp_bound2 = [&]() {                      // largest distance^2 that still matters to any voxel of the brick
-        float v = lim2;
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w)
+{
+    return __half22float2(__halves2half2(__ushort_as_half((unsigned short)(w & 0xffffu)), __ushort_as_half((unsigned short)(w >> 16))));
+}
+// outward rounding: the half box contains the double box
+__device__ __forceinline__ uint3 pack_box(const double* mn, const double* mx)
+{
+    __half l[3], h[3];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
-        return v * 1.001f;
-    };
-
-    const int64_t t0 = tri_off[mesh];
-    const int T = (int)(tri_off[mesh + 1] - t0);
-    const float4* Tm = tri + 4 * t0;
-    const float4* Fm = fast + 5 * t0;
-    const float4* Bm = aabb + 2 * t0;
-    const int ntile = (T + TILE - 1) / TILE;
-    u64 n_pairs = 0, n_tests = 0, n_faithful = 0;
-    int qn = 0;
-
-    // stage 2 on 32 queue entries starting at `from` (entries beyond `cnt` are idle lanes)
-    auto flush = [&](int from, int cnt) {
-        __syncwarp();
-        uint32_t ent = 0;
-        float d = INF;
-        const bool have = lane < cnt;
-        if (have) {
-            ent = q[from + lane];
-            const int o = ent & 31u;
-            const V3 go = node_pos(bi0 + (o & 3), bj0 + ((o >> 2) & 3), bk0 + (o >> 4), P);
-            d = point_triangle_distance(go, load_trirec(Tm + 4 * (int64_t)(ent >> 5)));
-            ++n_faithful;
-        }
-        for (int r = 0; r < cnt; ++r) {
-            const uint32_t er = __shfl_sync(0xffffffffu, ent, r);
-            const float dr = __shfl_sync(0xffffffffu, d, r);
-            const uint32_t tr = er >> 5;
-            if ((int)(er & 31u) == lane && (dr < best || (dr == best && best_t != 0xffffffffu && tr < best_t))) { best = dr; best_t = tr; }
-        }
-        __syncwarp();
-    };
-    auto issue_tile = [&](int tile) {               // thread 0: TMA bulk copy of one tile of boxes into stage tile % 3
-        const int sg = tile % 3;
-        const uint32_t bytes = (uint32_t)min(TILE, T - tile * TILE) * 32u;
-        mbar_expect_tx(&s_bar[sg], bytes);
-        bulk_g2s(s_box + sg * TILE * 2, Bm + 2 * (int64_t)tile * TILE, bytes, &s_bar[sg]);
-    };
-
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_init(&s_bar[2], 1);
-        mbar_fence_init();
-        s_count[0] = s_count[1] = s_count[2] = 0;
+    for (int a = 0; a < 3; ++a) {
+        l[a] = __float2half_rd(__double2float_rd(mn[a]));
+        h[a] = __float2half_ru(__double2float_ru(mx[a]));
     }
-    { const float wb = warp_bound2(); if (lane == 0) s_wb[warp] = wb; }
-    __syncthreads();
-    if (tid == 0) {
-        if (ntile > 0) issue_tile(0);
-        if (ntile > 1) issue_tile(1);
-    }
-    // One block barrier per tile: [phase A of tile it] barrier [phase B of tile it], with three box stages, two
-    // survivor lists and three counters so that a fast warp may already run phase A of the next tile.
-    for (int it = 0; it < ntile; ++it) {
-        const int sg = it % 3, lb = it & 1;
-        const int tn = min(TILE, T - it * TILE);
-        mbar_wait(&s_bar[sg], (it / 3) & 1);
-        const float4* box = s_box + sg * TILE * 2;
-        uint32_t* list = s_list + lb * TILE;
-
-        // ---- phase A: block-level cull against the largest running bound of the block's bricks
-        float blk_bound2 = s_wb[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) blk_bound2 = fmaxf(blk_bound2, s_wb[w]);
-        for (int q0 = warp * 32; q0 < tn; q0 += NT) {
-            int qq = q0 + lane;
-            bool pass = false;
-            if (qq < tn) {
-                pass = box_gap2(box[2 * qq], box[2 * qq + 1], blk_lo, blk_hi) <= blk_bound2;
-                ++n_tests;
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_count[sg], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)qq;
-            }
-        }
-        if (tid == 0) s_count[(it + 1) % 3] = 0;    // last read in phase B of tile it-2, next written after the barrier
-        __syncthreads();
-        if (tid == 0 && it + 2 < ntile) issue_tile(it + 2);   // its stage was last read in tile it-1
-        const int nlist = s_count[sg];
-
-        // ---- phase B: brick-level cull with the running bound, stage 1 on the survivors
-        for (int l0 = 0; l0 < nlist; l0 += 32) {
-            const float bound2 = warp_bound2();
-            uint32_t tq = 0;                         // the triangle's own index rides in lo.w of its box
-            bool pass = false;
-            if (l0 + lane < nlist) {
-                const int qq = (int)list[l0 + lane];
-                const float4 lo = box[2 * qq];
-                tq = __float_as_uint(lo.w);
-                pass = box_gap2(lo, box[2 * qq + 1], brick_lo, brick_hi) <= bound2;
-                ++n_tests;
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, pass);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t t = __shfl_sync(0xffffffffu, tq, src);
-                if (kPrefetchNext && m) {           // pull the next survivor's record while this one is rated
-                    const uint32_t tn2 = __shfl_sync(0xffffffffu, tq, __ffs(m) - 1);
-                    if (lane < 2) prefetch_l1(reinterpret_cast<const char*>(Fm + 5 * (int64_t)tn2) + lane * 64);
-                }
-                bool flagged;
-                float e2;
-                const float a2 = fast_dist2(gx, Fm + 5 * (int64_t)t, flagged, e2);
-                n_pairs += valid ? 1 : 0;
-                const bool cand = valid && (flagged || !(a2 - e2 > lim2));
-                if (!flagged && a2 + e2 < ub2) {     // new upper bound of the minimum: tighten the filter
-                    ub2 = a2 + e2;
-                    lim2 = fmaf(ub2, 1.002f, kappa);
-                }
-                const uint32_t cm = __ballot_sync(0xffffffffu, cand);
-                if (cm) {
-                    if (cand) q[qn + __popc(cm & ((1u << lane) - 1u))] = (t << 5) | (uint32_t)lane;
-                    qn += __popc(cm);
-                    if (qn >= 32) { qn -= 32; flush(qn, 32); }
-                }
-            }
-        }
-        { const float wb = warp_bound2(); if (lane == 0) s_wb[warp] = wb; }
-    }
-    if (qn > 0) flush(0, qn);
-    if (valid) {
-        float phi = (best_t == 0xffffffffu) ? far : best;
-        key[(int64_t)mesh * nvox + (i + (int64_t)ni * (j + (int64_t)nj * k))] = ((u64)__float_as_uint(phi) << 32) | best_t;
-    }
-    if (counter) {
-        if (n_faithful) atomicAdd(counter + 0, n_faithful);
-        if (n_pairs) atomicAdd(counter + 2, n_pairs);
-        if (n_tests) atomicAdd(counter + 3, n_tests);
-    }
+    return make_uint3(pack_h2(l[0], l[1]), pack_h2(l[2], h[0]), pack_h2(h[1], h[2]));
+}
+// squared distance (voxel units) between a packed box and the box [glo, ghi]; 0 when they overlap
+__device__ __forceinline__ float box_gap2(uint32_t w0, uint32_t w1, uint32_t w2, float3 glo, float3 ghi)
+{
+    const float2 a = unpack_h2(w0), b = unpack_h2(w1), c = unpack_h2(w2);   // lo.x lo.y | lo.z hi.x | hi.y hi.z
+    const float gx = fmaxf(0.f, fmaxf(a.x - ghi.x, glo.x - b.y));
+    const float gy = fmaxf(0.f, fmaxf(a.y - ghi.y, glo.y - c.x));
+    const float gz = fmaxf(0.f, fmaxf(b.x - ghi.z, glo.z - c.y));
+    return fmaf(gx, gx, fmaf(gy, gy, gz * gz));
 }
 
 struct Ws {
-    float4* tri; float4* fast; float4* aabb; int4* box; u64* key; uint32_t* parity; size_t bytes;
+    float4* tri; float4* fast; uint4* tmp; uint4* ent; u64* key; uint32_t* parity;
+    uint32_t* cell_start;     // [n_mesh][ncell + 2]: CSR starts relative to the mesh's first entry; [ncell] = large list, [ncell+1] = end
+    uint32_t* cursor;         // [n_mesh][ncell + 1]: counts (prep), then fill cursors
+    uint4* cellbox;           // [n_mesh][ncell]: union box of the cell's entries (3 words) + spare
+    uint32_t* dil;            // [n_mesh]: float bits of the largest overhang of a small triangle beyond its home cell
+    uint32_t* occ;            // [n_mesh][ceil(ncell / 32)]: bit = the cell holds at least one entry
+    size_t bytes;
 };
+
+__host__ __device__ inline int cells_of(int n) { return (n + kCell - 1) / kCell; }
+__host__ __device__ inline int64_t ncell_of(const g3d_tdf_params& p) { return (int64_t)cells_of(p.ni) * cells_of(p.nj) * cells_of(p.nk); }
 
 inline Ws carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p)
 {
     Ws w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
-    int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32;
+    const int64_t nvox = nvox_of(p), pw = (nvox + 31) / 32, ncell = ncell_of(p);
     w.tri = (float4*)take((size_t)total_tris * 64);
     w.fast = (float4*)take((size_t)total_tris * 80);
-    w.aabb = (float4*)take((size_t)total_tris * 32);
-    w.box = (int4*)take((size_t)total_tris * 16);
+    w.tmp = (uint4*)take((size_t)total_tris * 16);
+    w.ent = (uint4*)take((size_t)total_tris * 16);
     w.key = (u64*)take((size_t)n_mesh * nvox * 8);
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
+    w.cell_start = (uint32_t*)take((size_t)n_mesh * (ncell + 2) * 4);
+    w.cursor = (uint32_t*)take((size_t)n_mesh * (ncell + 1) * 4);
+    w.cellbox = (uint4*)take((size_t)n_mesh * ncell * 16);
+    w.dil = (uint32_t*)take((size_t)n_mesh * 4);
+    w.occ = (uint32_t*)take((size_t)n_mesh * ((ncell + 31) / 32) * 4);
     w.bytes = off;
     return w;
+}
+
+// the per-triangle part of the index, called by tdf_prep for a valid, finite triangle; f* are its corners in
+// grid coordinates (double, makelevelset3.cpp:131-133)
+__device__ __forceinline__ void index_triangle(const double* fp, const double* fq, const double* fr, int m, int64_t t,
+                                               const g3d_tdf_params& P, uint4* tmp, uint32_t* cursor, uint32_t* dil)
+{
+    const int nc[3] = { cells_of(P.ni), cells_of(P.nj), cells_of(P.nk) };
+    double mn[3], mx[3];
+    int c[3];
+    double over = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = fmin(fp[a], fmin(fq[a], fr[a]));
+        mx[a] = fmax(fp[a], fmax(fq[a], fr[a]));
+        double mid = 0.5 * (mn[a] + mx[a]) / (double)kCell;
+        mid = mid < 0.0 ? 0.0 : (mid > (double)(nc[a] - 1) ? (double)(nc[a] - 1) : mid);
+        c[a] = (int)mid;                                         // floor, mid >= 0
+        const double lo = (double)(kCell * c[a]), hi = lo + (double)kCell;
+        over = fmax(over, fmax(lo - mn[a], mx[a] - hi));
+    }
+    const int64_t ncell = (int64_t)nc[0] * nc[1] * nc[2];
+    const bool small = over <= (double)kSmallMax;
+    const int64_t cell = small ? (c[0] + (int64_t)nc[0] * (c[1] + (int64_t)nc[1] * c[2])) : ncell;
+    if (small) {                                                 // non-negative floats order like uints
+        const uint32_t ob = __float_as_uint(__double2float_ru(over < 0.0 ? 0.0 : over));
+        if (ob > *(volatile uint32_t*)(dil + m)) atomicMax(dil + m, ob);      // all triangles of a mesh share this word: look first
+    }
+    atomicAdd(cursor + (int64_t)m * (ncell + 1) + cell, 1u);
+    const uint3 b = pack_box(mn, mx);
+    tmp[t] = make_uint4(b.x, b.y, b.z, (uint32_t)cell);
+}
+
+// one CTA per mesh: counts -> exclusive starts; the counters become fill cursors (zero)
+__global__ void __launch_bounds__(256)
+exact_scan_kernel(uint32_t* __restrict__ cursor, uint32_t* __restrict__ cell_start, int64_t ncell)
+{
+    __shared__ uint32_t s_sum[256];
+    const int mesh = blockIdx.x, tid = threadIdx.x;
+    uint32_t* cnt = cursor + (int64_t)mesh * (ncell + 1);
+    uint32_t* st = cell_start + (int64_t)mesh * (ncell + 2);
+    const int64_t n = ncell + 1, per = (n + 255) / 256, lo = tid * per, hi = lo + per < n ? lo + per : n;
+    uint32_t sum = 0;
+    for (int64_t q = lo; q < hi; ++q) sum += cnt[q];
+    s_sum[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {                          // Hillis-Steele inclusive scan of the 256 partial sums
+        uint32_t v = tid >= d ? s_sum[tid - d] : 0u;
+        __syncthreads();
+        s_sum[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_sum[tid] - sum;
+    for (int64_t q = lo; q < hi; ++q) {
+        const uint32_t c = cnt[q];
+        st[q] = run;
+        cnt[q] = 0u;
+        run += c;
+    }
+    if (tid == 255) st[n] = s_sum[255];
+}
+
+__global__ void __launch_bounds__(256)
+exact_fill_kernel(const uint4* __restrict__ tmp, const int64_t* __restrict__ tri_off, int64_t total_tris, int n_mesh,
+                  int64_t ncell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cursor, uint4* __restrict__ ent)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_tris) return;
+    const uint4 e = tmp[t];
+    if (e.w == kNoCell) return;
+    int lo = 0, hi = n_mesh;                                     // tri_off[lo] <= t < tri_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tri_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int64_t tb = tri_off[lo];
+    const uint32_t pos = cell_start[(int64_t)lo * (ncell + 2) + e.w] + atomicAdd(cursor + (int64_t)lo * (ncell + 1) + e.w, 1u);
+    ent[tb + pos] = make_uint4(e.x, e.y, e.z, (uint32_t)(t - tb));
+}
+
+// one thread per cell: union of the cell's entry boxes (min / max of halves is exact)
+__global__ void __launch_bounds__(256)
+exact_cellbox_kernel(const uint4* __restrict__ ent, const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ cell_start,
+                     int64_t ncell, int64_t total_cells, uint4* __restrict__ cellbox, uint32_t* __restrict__ occ)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total_cells) return;
+    const int mesh = (int)(q / ncell);
+    const int64_t c = q - (int64_t)mesh * ncell;
+    const uint32_t* st = cell_start + (int64_t)mesh * (ncell + 2);
+    const uint32_t s = st[c], e = st[c + 1];
+    const float inf = __int_as_float(0x7f800000);
+    float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+    const uint4* E = ent + tri_off[mesh];
+    for (uint32_t p = s; p < e; ++p) {
+        const uint4 en = __ldg(E + p);
+        const float2 a = unpack_h2(en.x), b = unpack_h2(en.y), d = unpack_h2(en.z);
+        lx = fminf(lx, a.x); ly = fminf(ly, a.y); lz = fminf(lz, b.x);
+        hx = fmaxf(hx, b.y); hy = fmaxf(hy, d.x); hz = fmaxf(hz, d.y);
+    }
+    if (e > s) atomicOr(occ + (int64_t)mesh * ((ncell + 31) / 32) + (c >> 5), 1u << (c & 31));
+    cellbox[q] = make_uint4(pack_h2(__float2half_rd(lx), __float2half_rd(ly)), pack_h2(__float2half_rd(lz), __float2half_ru(hx)),
+                            pack_h2(__float2half_ru(hy), __float2half_ru(hz)), e - s);
+}
+
+// offset of the q-th cell of Chebyshev ring k >= 1 (24 k^2 + 2 cells): the two z faces, then the y faces without
+// their z edges, then the x faces without their y and z edges
+__device__ __forceinline__ void ring_offset(int k, int q, int& dx, int& dy, int& dz)
+{
+    const int w = 2 * k + 1, u = 2 * k - 1, A = w * w, B = w * u, C = u * u;
+    if (q < 2 * A) {
+        const int s = q >= A, r = q - s * A;
+        dz = s ? k : -k; dy = r / w - k; dx = r - (r / w) * w - k;
+    } else if (q < 2 * A + 2 * B) {
+        q -= 2 * A;
+        const int s = q >= B, r = q - s * B;
+        dy = s ? k : -k; dz = r / w - (k - 1); dx = r - (r / w) * w - k;
+    } else {
+        q -= 2 * A + 2 * B;
+        const int s = q >= C, r = q - s * C;
+        dx = s ? k : -k; dz = r / u - (k - 1); dy = r - (r / u) * u - (k - 1);
+    }
+}
+
+constexpr int kExactWarps = 4;            // warps per CTA
+constexpr int kRingTable = 124;           // rings 1 and 2 (26 + 98 cells) from a shared-memory table (+ the own cell)
+
+template <int MINB>
+__global__ void __launch_bounds__(kExactWarps * 32, MINB)
+tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fast, const uint4* __restrict__ ent,
+                  const uint32_t* __restrict__ cell_start, const uint4* __restrict__ cellbox, const uint32_t* __restrict__ occ,
+                  const uint32_t* __restrict__ dil, const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity,
+                  u64* __restrict__ key, g3d_tdf_params P, float R, float far, float kappa, int64_t n_groups, u64* counter)
+{
+    // Two warp-private queues turn two uneven filters into dense work:
+    //   pairs  (voxel, triangle) pairs that passed the per-voxel box test, waiting for stage 1 (32 at a time, one pair per lane)
+    //   queue  pairs whose stage-1 interval reaches below the voxel's bound, waiting for stage 2 (32 at a time)
+    // The group's work is ONE loop -- pick the next list, take 32 entries, test each entry's box against the 8 voxels,
+    // run whichever stage has a full batch -- so that each stage exists once in the instruction stream (inlined at
+    // every call site the kernel was twice the 32 KB instruction cache and mostly waited for instructions).
+    __shared__ uint32_t s_pairs[kExactWarps][64];
+    __shared__ uint32_t s_queue[kExactWarps][64];
+    __shared__ __align__(16) uint32_t s_ub[kExactWarps][8];   // per voxel of the group: float bits of ub2, the smallest a2 + e2 seen
+    __shared__ u64 s_best[kExactWarps][8];           // per voxel: float bits of the best faithful distance << 32 | its triangle
+    __shared__ int s_ring[kRingTable + 1];           // packed offsets (dx+8) | (dy+8)<<4 | (dz+8)<<8: own cell, rings 1 and 2
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int q = threadIdx.x; q < kRingTable + 1; q += kExactWarps * 32) {
+        int dx = 0, dy = 0, dz = 0;
+        if (q >= 27) ring_offset(2, q - 27, dx, dy, dz); else if (q >= 1) ring_offset(1, q - 1, dx, dy, dz);
+        s_ring[q] = (dx + 8) | ((dy + 8) << 4) | ((dz + 8) << 8);
+    }
+    __syncthreads();
+    uint32_t* pairs = s_pairs[warp];
+    uint32_t* qu = s_queue[warp];
+    volatile uint32_t* ubv = s_ub[warp];
+    const int ni = P.ni, nj = P.nj, nk = P.nk;
+    const int ncx = cells_of(ni), ncy = cells_of(nj), ncz = cells_of(nk);
+    const int64_t ncell = (int64_t)ncx * ncy * ncz, nvox = nvox_of(P), occ_words = (ncell + 31) / 32;
+    const float inv_dx = 1.0f / P.dx;
+    const float to_vox2 = inv_dx * inv_dx * 1.0001f * 1.001f;    // world distance^2 -> voxel units, rounded up, with the cull margin
+    const float INF = __int_as_float(0x7f800000);
+    u64 n_pairs = 0, n_tests = 0, n_faithful = 0;
+    enum { ST_LARGE, ST_BATCH, ST_REST, ST_RINGEND, ST_FINAL };
+
+    const int64_t wstride = (int64_t)gridDim.x * kExactWarps;
+    for (int64_t g = (int64_t)blockIdx.x * kExactWarps + warp; g < n_groups; g += wstride) {
+        const int mesh = (int)(g / ncell);
+        const int64_t cg = g - (int64_t)mesh * ncell;
+        const int cx = (int)(cg % ncx), cy = (int)((cg / ncx) % ncy), cz = (int)(cg / ((int64_t)ncx * ncy));
+        // lanes 0..7 own the group's voxels (lane = voxel): validity, sign, start value, result
+        const int i = kCell * cx + (lane & 1), j = kCell * cy + ((lane >> 1) & 1), k = kCell * cz + ((lane >> 2) & 1);
+        const bool valid = lane < 8 && i < ni && j < nj && k < nk;
+        bool inside = false;
+        if (valid) {                                    // running parity along i (makelevelset3.cpp:174-182)
+            const uint32_t* par = parity + (int64_t)mesh * ((nvox + 31) / 32);
+            const int64_t r0 = (int64_t)ni * (j + (int64_t)nj * k), r1 = r0 + i;
+            int cnt = 0;
+            for (int64_t w = r0 >> 5; w <= (r1 >> 5); ++w) {
+                uint32_t m = par[w];
+                if (w == (r0 >> 5)) m &= 0xffffffffu << (r0 & 31);
+                if (w == (r1 >> 5)) m &= 0xffffffffu >> (31 - (r1 & 31));
+                cnt += __popc(m);
+            }
+            inside = cnt & 1;
+        }
+        // like the reference's phi, the running minimum starts at `far` (makelevelset3.cpp:123): a triangle farther
+        // away than that never registers. Outside voxels may stop at the truncation radius instead.
+        const float start = inside ? far : fminf(R, far);
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        if (vmask == 0u) continue;                      // cannot happen for cells inside the grid
+        // stage 1 passes a pair to stage 2 iff a2 - e2 <= lim2 = 1.002 * ub2 + kappa, ub2 = smallest a2 + e2 seen (start^2 at first).
+        // stage 2 keeps (distance, triangle) as one 64-bit key per voxel: atomicMin is "smaller distance, then lower index";
+        // the initial key (start, 0) can only be beaten by a distance strictly below start, like the reference's d < phi.
+        const u64 key0 = (u64)__float_as_uint(start) << 32;
+        __syncwarp();
+        if (lane < 8) { ubv[lane] = __float_as_uint(start * start); s_best[warp][lane] = key0; }
+        __syncwarp();
+        // every lane keeps the 8 per-voxel cull bounds (voxel units^2; -1 for a voxel outside the grid) and their maximum
+        float vb[8], gb2;
+        auto load_bounds = [&]() {
+            uint32_t u[8];
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                         : "r"((uint32_t)__cvta_generic_to_shared(&s_ub[warp][0])) : "memory");
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                         : "r"((uint32_t)__cvta_generic_to_shared(&s_ub[warp][4])) : "memory");
+            gb2 = -1.f;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                vb[b] = ((vmask >> b) & 1u) ? fmaf(__uint_as_float(u[b]), 1.002f, kappa) * to_vox2 : -1.f;
+                gb2 = fmaxf(gb2, vb[b]);
+            }
+        };
+        load_bounds();
+        const float x0 = (float)(kCell * cx), y0 = (float)(kCell * cy), z0 = (float)(kCell * cz);
+        const float3 glo = make_float3(x0, y0, z0);
+        const float3 ghi = make_float3((float)min(kCell * cx + kCell - 1, ni - 1), (float)min(kCell * cy + kCell - 1, nj - 1),
+                                       (float)min(kCell * cz + kCell - 1, nk - 1));
+
+        const int64_t t0 = tri_off[mesh];
+        const float4* Tm = tri + 4 * t0;
+        const float4* Fm = fast + 5 * t0;
+        const uint4* Em = ent + t0;
+        const uint32_t* CS = cell_start + (int64_t)mesh * (ncell + 2);
+        const uint4* CB = cellbox + (int64_t)mesh * ncell;
+        // a small triangle overhangs its home cell by at most D voxels (+ the outward rounding of the half-precision
+        // boxes: one ulp at the grid's far end, 11 significant bits); ring k's cells are at least 2k - 2 voxels away
+        const float D = __uint_as_float(__ldg(dil + mesh)) * 1.01f + 0.05f + (float)max(ni, max(nj, nk)) * (1.01f / 1024.f);
+        const int kmax = max(max(cx, ncx - 1 - cx), max(max(cy, ncy - 1 - cy), max(cz, ncz - 1 - cz)));
+
+        // anything at all nearby? the large list's length and the occupancy bits of the 5 x 5 x 5 cells around the group
+        // (one (y, z) row of cells per lane) decide whether rings 0..2 need a visit
+        uint32_t n_large = 0;
+        bool near = false;
+        {
+            bool hit = false;
+            if (lane < 25) {
+                const int y = cy + lane % 5 - 2, z = cz + lane / 5 - 2;
+                if (y >= 0 && z >= 0 && y < ncy && z < ncz) {
+                    const uint32_t* OC = occ + (int64_t)mesh * occ_words;
+                    const int xs = max(cx - 2, 0), nb = min(cx + 2, ncx - 1) - xs + 1;
+                    const int64_t b0 = xs + (int64_t)ncx * (y + (int64_t)ncy * z);
+                    const int sh = (int)(b0 & 31);
+                    uint32_t w = __ldg(OC + (b0 >> 5)) >> sh;
+                    if (sh + nb > 32) w |= __ldg(OC + (b0 >> 5) + 1) << (32 - sh);
+                    hit = (w & ((1u << nb) - 1u)) != 0u;
+                }
+            } else if (lane == 31) {
+                n_large = __ldg(CS + ncell + 1) - __ldg(CS + ncell);
+            }
+            near = __any_sync(0xffffffffu, hit);
+            n_large = __shfl_sync(0xffffffffu, n_large, 31);
+        }
+
+        int pqn = 0, qn = 0;                             // fills of pairs / queue, warp-uniform
+        // the list being walked: the concatenation of one list per lane (start st, length cnt, exclusive offset excl)
+        uint32_t st = 0, cnt = 0, excl = 0, total = 0, pos = 0;
+        int single = -1;
+        uint32_t rest_cnt = 0;                           // the batch's other cells, admitted after the nearest one
+        float rest_g2 = INF;
+        int state = n_large ? ST_LARGE : ST_BATCH, kr = near ? 0 : 3, q0 = 0;
+        if (!near) {
+            const float lb3 = 4.f - D;
+            if (kr > kmax || (lb3 > 0.f && lb3 * lb3 > gb2)) state = n_large ? ST_LARGE : ST_FINAL;
+        }
+        bool drained = state == ST_FINAL;                // nothing was queued yet: no drain needed to finish
+        for (;;) {
+            bool drain = false, final = false;
+            uint32_t vm = 0, tid = 0;                    // this lane's entry: voxels (bit mask) whose box test it passed, triangle
+            if (pos >= total) {
+                // ---- pick the next list (warp-uniform control flow)
+                bool fresh = false;
+                if (state == ST_LARGE) {                 // triangles too big for the grid: every group looks at all of them
+                    cnt = 0;
+                    if (lane == 0) { st = __ldg(CS + ncell); cnt = n_large; }
+                    state = ST_BATCH;
+                    if (!near) {
+                        const float lb3 = 4.f - D;
+                        if (kr > kmax || (lb3 > 0.f && lb3 * lb3 > gb2)) state = ST_FINAL;
+                    }
+                    fresh = true;
+                } else if (state == ST_BATCH) {
+                    const int n = kr == 0 ? 1 : 24 * kr * kr + 2;
+                    if (q0 >= n) {
+                        state = ST_RINGEND;
+                    } else {
+                        // up to 32 cells of ring kr (lane = cell): boxes and list starts of the whole batch in one round trip
+                        const int q = q0 + lane;
+                        int dx = 0, dy = 0, dz = 0;
+                        if (q < n) {
+                            if (kr <= 2) {
+                                const int o = s_ring[(kr == 2 ? 27 : kr) + q];
+                                dx = (o & 15) - 8; dy = ((o >> 4) & 15) - 8; dz = ((o >> 8) & 15) - 8;
+                            } else {
+                                ring_offset(kr, q, dx, dy, dz);
+                            }
+                        }
+                        const int ccx = cx + dx, ccy = cy + dy, ccz = cz + dz;
+                        uint32_t keyv = 0xffffffffu;
+                        cnt = 0; rest_cnt = 0; rest_g2 = INF;
+                        if (q < n && ccx >= 0 && ccy >= 0 && ccz >= 0 && ccx < ncx && ccy < ncy && ccz < ncz) {
+                            const int64_t cid = ccx + (int64_t)ncx * (ccy + (int64_t)ncy * ccz);
+                            const uint4 cb = __ldg(CB + cid);
+                            st = __ldg(CS + cid);
+                            ++n_tests;
+                            if (cb.w) {
+                                rest_g2 = box_gap2(cb.x, cb.y, cb.z, glo, ghi);
+                                if (rest_g2 <= gb2) { keyv = (__float_as_uint(rest_g2) & ~31u) | (uint32_t)lane; rest_cnt = cb.w; }
+                            }
+                        }
+                        const uint32_t kmin = __reduce_min_sync(0xffffffffu, keyv);
+                        if (kmin == 0xffffffffu) {
+                            q0 += 32;                    // nothing of this batch is within reach
+                        } else {                         // the nearest cell first, on its own: it tightens the bound
+                            if (lane == (int)(kmin & 31u)) { cnt = rest_cnt; rest_cnt = 0; }
+                            state = __any_sync(0xffffffffu, rest_cnt != 0) ? ST_REST : ST_BATCH;
+                            if (state == ST_BATCH) q0 += 32;
+                            fresh = true;
+                        }
+                    }
+                } else if (!drained) {                   // ST_REST / ST_RINGEND / ST_FINAL: everything waiting goes through first
+                    drain = true;
+                    final = state == ST_FINAL;
+                    drained = true;
+                } else {
+                    drained = false;
+                    if (state == ST_REST) {              // the other cells of the batch, against the tightened bound
+                        cnt = rest_g2 <= gb2 ? rest_cnt : 0u;
+                        state = ST_BATCH;
+                        q0 += 32;
+                        fresh = true;
+                    } else if (state == ST_RINGEND) {
+                        ++kr;
+                        q0 = 0;
+                        state = ST_BATCH;
+                        const float lb = (float)(2 * kr - 2) - D;
+                        if (kr > kmax || (lb > 0.f && lb * lb > gb2)) state = ST_FINAL;
+                    } else {
+                        break;                           // ST_FINAL, drained: the group is done
+                    }
+                }
+                if (fresh) {                             // inclusive scan of the list lengths over the lanes
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    total = __shfl_sync(0xffffffffu, incl, 31);
+                    excl = incl - cnt;
+                    pos = 0;
+                    const uint32_t owners = __ballot_sync(0xffffffffu, cnt != 0u);
+                    single = (owners & (owners - 1u)) == 0u && owners ? __ffs(owners) - 1 : -1;   // one lane owns the whole list: no search
+                }
+            }
+            if (pos < total) {
+                // ---- the next 32 entries of the list: this lane's entry box against each of the 8 voxels with that voxel's bound
+                const uint32_t q = pos + lane;
+                pos += 32;
+                // owner = the last lane whose exclusive offset is <= q (a lane with an empty list shares its successor's
+                // offset and loses to it)
+                int own = single;
+                if (single < 0) {
+                    own = 0;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        const int c2 = own + d;
+                        const uint32_t ex = __shfl_sync(0xffffffffu, excl, c2 & 31);
+                        if (ex <= q) own = c2;
+                    }
+                }
+                const uint32_t ost = __shfl_sync(0xffffffffu, st, own), oex = __shfl_sync(0xffffffffu, excl, own);
+                if (q < total) {
+                    const uint4 en = __ldg(Em + ost + (q - oex));
+                    tid = en.w;
+                    ++n_tests;
+                    const float2 a = unpack_h2(en.x), b = unpack_h2(en.y), c = unpack_h2(en.z);   // lo.x lo.y | lo.z hi.x | hi.y hi.z
+                    // squared gap per axis for the two node coordinates of the group on that axis
+                    float ex[2], ey[2], ez[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float gx = x0 + (float)h, gy = y0 + (float)h, gz = z0 + (float)h;
+                        const float tx = fmaxf(0.f, fmaxf(a.x - gx, gx - b.y));
+                        const float ty = fmaxf(0.f, fmaxf(a.y - gy, gy - c.x));
+                        const float tz = fmaxf(0.f, fmaxf(b.x - gz, gz - c.y));
+                        ex[h] = tx * tx; ey[h] = ty * ty; ez[h] = tz * tz;
+                    }
+#pragma unroll
+                    for (int vx = 0; vx < 8; ++vx)
+                        if (ex[vx & 1] + ey[(vx >> 1) & 1] + ez[vx >> 2] <= vb[vx]) vm |= 1u << vx;
+                }
+            }
+            // ---- pairs of this batch to the queue, voxel by voxel; whichever stage has a full batch (or anything at all when
+            // draining, in the extra round vx == 8) runs, the later stage first so that no queue overflows; each stage exists once
+            uint32_t um = __reduce_or_sync(0xffffffffu, vm);          // voxels that got at least one pair from this batch
+            if (!drain && um == 0u) continue;
+            for (;;) {
+                if (um) {
+                    const int vx = __ffs(um) - 1;
+                    um &= um - 1u;
+                    const bool mine = (vm >> vx) & 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                    if (mine) pairs[pqn + __popc(m & lt)] = (tid << 3) | (uint32_t)vx;
+                    pqn += __popc(m);
+                }
+                const bool last = um == 0u && drain;
+                if (pqn < 32 && !last) { if (um == 0u) break; continue; }
+                for (;;) {
+                    const int act = qn >= 32 ? 2 : pqn >= 32 ? 1 : !last ? 0 : pqn > 0 ? 1 : (final && qn > 0) ? 2 : 0;
+                    if (act == 0) break;
+                    __syncwarp();
+                    if (act == 1) {
+                        // stage 1 on up to 32 (voxel, triangle) pairs, one pair per lane
+                        const int c = min(pqn, 32);
+                        pqn -= c;
+                        bool cand = false;
+                        uint32_t pr = 0;
+                        if (lane < c) {
+                            pr = pairs[pqn + lane];
+                            const int o = pr & 7u;
+                            const V3 go = node_pos(kCell * cx + (o & 1), kCell * cy + ((o >> 1) & 1), kCell * cz + (o >> 2), P);
+                            bool flagged;
+                            float e2;
+                            const float a2 = fast_dist2(go, Fm + 5 * (int64_t)(pr >> 3), flagged, e2);
+                            ++n_pairs;
+                            const float ub = __uint_as_float(ubv[o]);
+                            cand = flagged || !(a2 - e2 > fmaf(ub, 1.002f, kappa));
+                            if (!flagged && a2 + e2 < ub) atomicMin(&s_ub[warp][o], __float_as_uint(a2 + e2));   // non-negative floats order like uints
+                        }
+                        const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+                        if (cand) qu[qn + __popc(cm & lt)] = pr;
+                        qn += __popc(cm);
+                        __syncwarp();
+                        load_bounds();
+                    } else {
+                        // stage 2 on up to 32 queued pairs: the bit-faithful function decides
+                        const int c = min(qn, 32);
+                        qn -= c;
+                        uint32_t e = 0;
+                        float d = INF;
+                        if (lane < c) {
+                            e = qu[qn + lane];
+                            const int o = e & 7u;
+                            const V3 go = node_pos(kCell * cx + (o & 1), kCell * cy + ((o >> 1) & 1), kCell * cz + (o >> 2), P);
+                            d = point_triangle_distance(go, load_trirec(Tm + 4 * (int64_t)(e >> 3)));
+                            ++n_faithful;
+                        }
+                        if (lane < c) atomicMin(&s_best[warp][e & 7u], ((u64)__float_as_uint(d) << 32) | (e >> 3));
+                    }
+                }
+                if (um == 0u) break;
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            const u64 kb = s_best[warp][lane];
+            key[(int64_t)mesh * nvox + (i + (int64_t)ni * (j + (int64_t)nj * k))] =
+                kb == key0 ? (((u64)__float_as_uint(far) << 32) | 0xffffffffull) : kb;
+        }
+        __syncwarp();
+    }
+    if (counter) {
+        if (n_faithful) atomicAdd(counter + 0, n_faithful);
+        if (n_pairs) atomicAdd(counter + 2, n_pairs);
+        if (n_tests) atomicAdd(counter + 3, n_tests);
+    }
 }
 
 }  // namespace exact
