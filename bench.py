@@ -643,7 +643,11 @@ def run_b200(args, rank, world, local):
     if not args.no_e2e:
         ctx = C.c_void_p()
         _lib.check(L.g3d_context_create(local, C.byref(ctx)))
+        # every table has 10,830 vertices: the indices travel as 16-bit words (g3d_tdf_batch_host_submit_u16), a third less H2D
+        T16 = T.astype(np.uint16)
+        assert int(T.max()) < 65536
         hV, hT = torch.from_numpy(V).pin_memory(), torch.from_numpy(T.view(np.int32)).pin_memory()
+        hT16 = torch.from_numpy(T16.view(np.int16)).pin_memory()
         hsdf = torch.empty((M, DIM, DIM, DIM), dtype=torch.float32).pin_memory()
         hbits = torch.empty((M, DIM ** 3 // 32), dtype=torch.int32).pin_memory()
         hstat = torch.empty((M,), dtype=torch.int32).pin_memory()
@@ -670,17 +674,17 @@ def run_b200(args, rank, world, local):
         # The loop a dataset generator runs: submit batch k+1, then wait for batch k (two sets of host buffers). Every
         # step still copies its own inputs to the device and its own results back inside the timed region; the copies
         # of neighbouring steps overlap the kernels instead of waiting for them.
-        hV2, hT2 = hV.clone().pin_memory(), hT.clone().pin_memory()
+        hV2, hT2 = hV.clone().pin_memory(), hT16.clone().pin_memory()
         hsdf2, hbits2, hstat2 = torch.empty_like(hsdf).pin_memory(), torch.empty_like(hbits).pin_memory(), torch.empty_like(hstat).pin_memory()
         o2 = _lib.TdfOutputs()
         o2.sdf, o2.occ_bits, o2.status = hsdf2.data_ptr(), hbits2.data_ptr(), hstat2.data_ptr()
-        sets = ((hV, hT, o), (hV2, hT2, o2))
+        sets = ((hV, hT16, o), (hV2, hT2, o2))
 
         def submit(k):
             v_, t_, o_ = sets[k & 1]
             tk = C.c_int32(-1)
-            _lib.check(L.g3d_tdf_batch_host_submit(ctx, v_.data_ptr(), voff.ctypes.data, t_.data_ptr(), toff.ctypes.data, M,
-                                                   C.byref(p), C.byref(o_), C.byref(tk)))
+            _lib.check(L.g3d_tdf_batch_host_submit_u16(ctx, v_.data_ptr(), voff.ctypes.data, t_.data_ptr(), toff.ctypes.data, M,
+                                                       C.byref(p), C.byref(o_), C.byref(tk)))
             return tk.value
 
         def pipelined(nsteps):
@@ -702,12 +706,14 @@ def run_b200(args, rank, world, local):
         if args.steps > 1:
             assert torch.equal(hsdf, hsdf2)                  # both buffer sets received the same batch's results
         e2e = {"value": total_vox / dt, "unit": "voxels/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(V.nbytes + T.nbytes + voff.nbytes + toff.nbytes),
+               "h2d_bytes_per_step": int(V.nbytes + T16.nbytes + voff.nbytes + toff.nbytes),
                "d2h_bytes_per_step": int(hsdf.numel() * 4 + hbits.numel() * 4 + hstat.numel() * 4),
-               "api": "g3d_tdf_batch_host_submit / _wait, two batches in flight (pinned host buffers; outputs: sdf + "
-                      "occupancy bits + status); every step's H2D and D2H copies are inside the timed region",
+               "api": "g3d_tdf_batch_host_submit_u16 / _wait, two batches in flight (pinned host buffers; 16-bit triangle indices; "
+                      "outputs requested: sdf + occupancy bits + status -- tdf and tdflog are one clamp / log away from sdf and a "
+                      "caller that wants them passes their pointers too); every step's H2D and D2H copies are inside the timed region",
+               "host_bytes_per_s": (V.nbytes + T16.nbytes + hsdf.numel() * 4 + hbits.numel() * 4) / dt,
                "sync": {"value": total_vox / dt_sync, "ms_per_step": dt_sync * 1e3,
-                        "api": "g3d_tdf_batch_host, one call per step, returns when the results are on the host"},
+                        "api": "g3d_tdf_batch_host (32-bit indices), one call per step, returns when the results are on the host"},
                "numa_bind": numa}
         L.g3d_context_destroy(ctx)
         # per host-path step: fill, 4 x (prep, band init), order, sweep, 4 x finalize (exact: fill, 4 x prep, exact, 4 x finalize)

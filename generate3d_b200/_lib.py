@@ -50,6 +50,8 @@ SYMBOLS = {
     "g3d_tdf_batch_host_submit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(TdfParams),
                                             C.POINTER(TdfOutputs), C.POINTER(C.c_int32)]),
     "g3d_tdf_batch_host_wait": (C.c_int, [_vp, _i32]),
+    "g3d_tdf_batch_host_submit_u16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(TdfParams),
+                                                C.POINTER(TdfOutputs), C.POINTER(C.c_int32)]),
     "g3d_raycast_batch_host": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _i32,
                                          _vp, _vp, _vp]),
     "g3d_dfgen_geometry": (C.c_int, [_i32, _i32, _i32, _vp, _vp, C.POINTER(TdfParams), _vp]),

@@ -145,17 +145,25 @@ static int run_batch(const char* list_path, int dim, int padding, int unit, int 
                   HostSet::grow(H.sdf, H.cg, (size_t)m * nvox) && HostSet::grow(H.status, H.cm, (size_t)m);
         if (ok && occ_txt) ok = HostSet::grow(H.occ, H.co, (size_t)m * nvox);
         if (!ok) { fprintf(stderr, "dfgen: %s\n", g3d_last_error()); return false; }
+        bool idx16 = true;                          // 16-bit indices when every mesh of the batch allows it: a third less PCIe traffic
+        for (int q = 0; q < m; ++q) idx16 = idx16 && jobs[H.jobs[q]].nv <= 65535;
         parallel_for(m, threads, [&](int q) {
             Job& j = jobs[H.jobs[q]];
             memcpy(H.v + 3 * H.voff[q], j.v, (size_t)j.nv * 12);
-            memcpy(H.t + 3 * H.toff[q], j.t, (size_t)j.nt * 12);
+            if (idx16) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(H.t) + 3 * H.toff[q];
+                for (int64_t e = 0; e < 3 * j.nt; ++e) dst[e] = j.t[e] > 0xffffu ? (uint16_t)0xffffu : (uint16_t)j.t[e];   // an out-of-range index stays out of range (nv <= 65535)
+            } else {
+                memcpy(H.t + 3 * H.toff[q], j.t, (size_t)j.nt * 12);
+            }
             printf("file: %s\nn-faces: %lld\nn-verts: %lld\n", j.mesh.c_str(), (long long)j.nt, (long long)j.nv);
             release(j);
         });
         g3d_tdf_outputs out;
         memset(&out, 0, sizeof out);
         out.sdf = H.sdf; out.occ_f32 = occ_txt ? H.occ : nullptr; out.status = H.status;
-        rc = g3d_tdf_batch_host_submit(ctx, H.v, H.voff.data(), H.t, H.toff.data(), m, &P[s], &out, &H.ticket);
+        rc = idx16 ? g3d_tdf_batch_host_submit_u16(ctx, H.v, H.voff.data(), reinterpret_cast<const uint16_t*>(H.t), H.toff.data(), m, &P[s], &out, &H.ticket)
+                   : g3d_tdf_batch_host_submit(ctx, H.v, H.voff.data(), H.t, H.toff.data(), m, &P[s], &out, &H.ticket);
         if (rc != G3D_OK) {
             fprintf(stderr, "dfgen: batch of %d models failed: %s\n", m, g3d_last_error());
             n_fail += m;

@@ -172,7 +172,7 @@ int g3d_tdf_batch(const float* verts, const int64_t* vert_off, int64_t total_ver
     cudaStream_t s = (cudaStream_t)cuda_stream;
     int rc = tdf_begin(total_verts, total_tris, n_mesh, *params, *out, workspace, workspace_bytes, s);
     if (rc != G3D_OK) return rc;
-    rc = tdf_stage_tris(verts, vert_off, tris, tri_off, 0, total_tris, 0, n_mesh, total_tris, n_mesh, *params, *out, workspace, s);
+    rc = tdf_stage_tris(verts, vert_off, tris, 4, tri_off, 0, total_tris, 0, n_mesh, total_tris, n_mesh, *params, *out, workspace, s);
     if (rc != G3D_OK) return rc;
     rc = tdf_solve(tri_off, total_tris, n_mesh, *params, workspace, s);
     if (rc != G3D_OK) return rc;
@@ -319,9 +319,9 @@ void g3d_context_destroy(g3d_context* c)
 
 size_t g3d_context_arena_bytes(const g3d_context* c) { return c ? c->arena_bytes[0] + c->arena_bytes[1] : 0; }
 
-int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t* vert_off, const uint32_t* tris,
-                              const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
-                              const g3d_tdf_outputs* out, int32_t* ticket)
+static int tdf_host_submit(g3d_context* c, const float* verts, const int64_t* vert_off, const void* tris, int index_bytes,
+                           const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
+                           const g3d_tdf_outputs* out, int32_t* ticket)
 {
     if (!c || !params || !out || !ticket) { set_error("tdf_host: NULL argument"); return G3D_ERR_INVALID; }
     *ticket = -1;
@@ -343,11 +343,11 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
     const int64_t nvox = (int64_t)params->ni * params->nj * params->nk, pw = (nvox + 31) / 32;
     const size_t ws_bytes = g3d_tdf_workspace_bytes(n_mesh, nv, nt, params);
 
-    auto layout = [&](char* base, g3d_tdf_outputs& d, float*& dv, int64_t*& dvo, uint32_t*& dt, int64_t*& dto, void*& ws) {
+    auto layout = [&](char* base, g3d_tdf_outputs& d, float*& dv, int64_t*& dvo, char*& dt, int64_t*& dto, void*& ws) {
         Carver k(base);
         dv = k.take<float>((size_t)nv * 3);
         dvo = k.take<int64_t>((size_t)n_mesh + 1);
-        dt = k.take<uint32_t>((size_t)nt * 3);
+        dt = k.take<char>((size_t)nt * 3 * index_bytes);
         dto = k.take<int64_t>((size_t)n_mesh + 1);
         d.sdf = out->sdf ? k.take<float>((size_t)n_mesh * nvox) : nullptr;
         d.tdf = out->tdf ? k.take<float>((size_t)n_mesh * nvox) : nullptr;
@@ -360,7 +360,7 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
         return k.off;
     };
     g3d_tdf_outputs d{};
-    float* dv; int64_t* dvo; uint32_t* dt; int64_t* dto; void* ws;
+    float* dv; int64_t* dvo; char* dt; int64_t* dto; void* ws;
     size_t need = layout(nullptr, d, dv, dvo, dt, dto, ws);
     char* base = arena_reserve(c, need, slot);
     if (!base) return G3D_ERR_CUDA;
@@ -387,7 +387,8 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
         const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1);
         const int64_t v0 = vert_off[m0], v1 = vert_off[m1], t0 = tri_off[m0], t1 = tri_off[m1];
         if (v1 > v0) G3D_TRY_BAIL(cudaMemcpyAsync(dv + 3 * v0, verts + 3 * v0, (size_t)(v1 - v0) * 12, cudaMemcpyHostToDevice, c->s_in));
-        if (t1 > t0) G3D_TRY_BAIL(cudaMemcpyAsync(dt + 3 * t0, tris + 3 * t0, (size_t)(t1 - t0) * 12, cudaMemcpyHostToDevice, c->s_in));
+        if (t1 > t0) G3D_TRY_BAIL(cudaMemcpyAsync(dt + (size_t)3 * t0 * index_bytes, (const char*)tris + (size_t)3 * t0 * index_bytes,
+                                                  (size_t)(t1 - t0) * 3 * index_bytes, cudaMemcpyHostToDevice, c->s_in));
         G3D_TRY_BAIL(cudaEventRecord(ev_in[ch], c->s_in));
     }
     G3D_TRY_BAIL(cudaStreamWaitEvent(s, ev_in[0], 0));           // the offset arrays precede chunk 0 on the input stream
@@ -396,7 +397,7 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
     for (int ch = 0; ch < nch; ++ch) {
         const int m0 = chunk_lo(ch), m1 = chunk_lo(ch + 1);
         G3D_TRY_BAIL(cudaStreamWaitEvent(s, ev_in[ch], 0));
-        rc = tdf_stage_tris(dv, dvo, dt, dto, tri_off[m0], tri_off[m1], m0, m1, nt, n_mesh, *params, d, ws, s);
+        rc = tdf_stage_tris(dv, dvo, dt, index_bytes, dto, tri_off[m0], tri_off[m1], m0, m1, nt, n_mesh, *params, d, ws, s);
         if (rc != G3D_OK) return bail(rc);
     }
     rc = tdf_solve(dto, nt, n_mesh, *params, ws, s);
@@ -422,6 +423,26 @@ int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t*
     *ticket = slot;
     return G3D_OK;
 #undef G3D_TRY_BAIL
+}
+
+int g3d_tdf_batch_host_submit(g3d_context* c, const float* verts, const int64_t* vert_off, const uint32_t* tris,
+                              const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
+                              const g3d_tdf_outputs* out, int32_t* ticket)
+{
+    return tdf_host_submit(c, verts, vert_off, tris, 4, tri_off, n_mesh, params, out, ticket);
+}
+
+int g3d_tdf_batch_host_submit_u16(g3d_context* c, const float* verts, const int64_t* vert_off, const uint16_t* tris,
+                                  const int64_t* tri_off, int32_t n_mesh, const g3d_tdf_params* params,
+                                  const g3d_tdf_outputs* out, int32_t* ticket)
+{
+    if (n_mesh > 0 && vert_off)
+        for (int m = 0; m < n_mesh; ++m)
+            if (vert_off[m + 1] - vert_off[m] > 65536) {
+                set_error("tdf_host: mesh %d has %lld vertices; 16-bit indices address 65,536", m, (long long)(vert_off[m + 1] - vert_off[m]));
+                return G3D_ERR_INVALID;
+            }
+    return tdf_host_submit(c, verts, vert_off, tris, 2, tri_off, n_mesh, params, out, ticket);
 }
 
 int g3d_tdf_batch_host_wait(g3d_context* c, int32_t ticket)

@@ -23,7 +23,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t tdf_workspace_bytes(int32_t n_mesh, int64_t total_tris, const g3d_tdf_params& p);
 int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
               const g3d_tdf_outputs& out, void* ws, size_t ws_bytes, cudaStream_t stream);
-int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* tris, const int64_t* tri_off,
+int tdf_stage_tris(const float* verts, const int64_t* vert_off, const void* tris, int index_bytes, const int64_t* tri_off,
                    int64_t t0, int64_t t1, int32_t m0, int32_t m1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
                    const g3d_tdf_outputs& out, void* ws, cudaStream_t stream);
 int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p, void* ws,

@@ -169,9 +169,11 @@ __device__ __forceinline__ int mesh_of(const int64_t* off, int n_mesh, int64_t t
     return lo;
 }
 
+// IT = uint32_t, or uint16_t for the host path's compact index arrays (every mesh below 65,536 vertices)
+template <typename IT>
 __global__ void __launch_bounds__(256)
 tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ vert_off,
-                const uint32_t* __restrict__ tris, const int64_t* __restrict__ tri_off,
+                const IT* __restrict__ tris, const int64_t* __restrict__ tri_off,
                 int64_t t_first, int64_t total_tris, int n_mesh, g3d_tdf_params P, float4* __restrict__ tri_out,
                 int4* __restrict__ box_out, uint32_t* __restrict__ parity, int32_t* status,
                 float4* __restrict__ fast_out, uint4* __restrict__ tmp_out, uint32_t* __restrict__ cell_count,
@@ -1073,22 +1075,31 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     return G3D_OK;
 }
 
-int tdf_stage_tris(const float* verts, const int64_t* vert_off, const uint32_t* tris, const int64_t* tri_off,
+int tdf_stage_tris(const float* verts, const int64_t* vert_off, const void* tris, int index_bytes, const int64_t* tri_off,
                    int64_t t0, int64_t t1, int32_t m0, int32_t m1, int64_t total_tris, int32_t n_mesh, const g3d_tdf_params& p,
                    const g3d_tdf_outputs& out, void* ws, cudaStream_t stream)
 {
+    if (index_bytes != 4 && index_bytes != 2) { set_error("tdf: triangle indices must be 2 or 4 bytes wide"); return G3D_ERR_INVALID; }
     if (n_mesh == 0 || t1 <= t0) return G3D_OK;
     const int sms = sm_count();
     const float far = (float)(p.ni + p.nj + p.nk) * p.dx;
     if (p.mode == G3D_MODE_EXACT) {
         exact::Ws w = exact::carve(ws, n_mesh, total_tris, p);
-        tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, nullptr, w.parity, out.status, w.fast, w.tmp, w.cursor, w.dil);
+        if (index_bytes == 2)
+            tdf_prep_kernel<uint16_t><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
+                verts, vert_off, (const uint16_t*)tris, tri_off, t0, t1, n_mesh, p, w.tri, nullptr, w.parity, out.status, w.fast, w.tmp, w.cursor, w.dil);
+        else
+            tdf_prep_kernel<uint32_t><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
+                verts, vert_off, (const uint32_t*)tris, tri_off, t0, t1, n_mesh, p, w.tri, nullptr, w.parity, out.status, w.fast, w.tmp, w.cursor, w.dil);
         prof_mark(ST_PREP, stream);
     } else {
         TdfWs w = carve(ws, n_mesh, total_tris, p);
-        tdf_prep_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
-            verts, vert_off, tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr);
+        if (index_bytes == 2)
+            tdf_prep_kernel<uint16_t><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
+                verts, vert_off, (const uint16_t*)tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr);
+        else
+            tdf_prep_kernel<uint32_t><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
+                verts, vert_off, (const uint32_t*)tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr);
         prof_mark(ST_PREP, stream);
         // [t0, t1) are the triangles of meshes [m0, m1). Batches of small grids: one CTA per 16^3 block of a mesh, keys in
         // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel, and so do

@@ -780,3 +780,38 @@ def test_cadvoxelization_isolates_a_failing_batch_and_writes_ply(g3d, oracle, tm
         ref = tmp_path / "ref.df"
         oracle.write_df(str(ref), want[mid]["sdf"], want[mid]["grid2world"])
         assert a == ref.read_bytes()
+
+
+def test_host_abi_u16_indices_equal_u32(g3d):
+    """g3d_tdf_batch_host_submit_u16: the same batch with 16-bit triangle indices gives the same bits; a mesh with more
+    than 65,536 vertices is refused with a message."""
+    V, voff, T, toff = S.table_batch(70, 3, first_seed=400)
+    L = g3d.lib()
+    ctx = C.c_void_p()
+    g3d.check(L.g3d_context_create(0, C.byref(ctx)))
+    p = g3d.TdfParams()
+    g2w = np.zeros(16, np.float32)
+    g3d.check(L.g3d_dfgen_geometry(32, 0, 1, None, None, C.byref(p), g2w.ctypes.data))
+    p.trunc, p.occ_thresh, p.mode = 3.0, 1.0, 0
+    res = []
+    for bits in (32, 16):
+        sdf = np.empty((70, 32, 32, 32), np.float32)
+        ct = np.empty((70, 32, 32, 32), np.int32)
+        o = g3d.TdfOutputs()
+        o.sdf, o.closest_tri = sdf.ctypes.data, ct.ctypes.data
+        tk = C.c_int32(-1)
+        if bits == 32:
+            g3d.check(L.g3d_tdf_batch_host_submit(ctx, V.ctypes.data, voff.ctypes.data, T.ctypes.data, toff.ctypes.data, 70, C.byref(p), C.byref(o), C.byref(tk)))
+        else:
+            T16 = np.ascontiguousarray(T.astype(np.uint16))
+            g3d.check(L.g3d_tdf_batch_host_submit_u16(ctx, V.ctypes.data, voff.ctypes.data, T16.ctypes.data, toff.ctypes.data, 70, C.byref(p), C.byref(o), C.byref(tk)))
+        g3d.check(L.g3d_tdf_batch_host_wait(ctx, tk.value))
+        res.append((sdf, ct))
+    assert np.array_equal(_bits(res[0][0]), _bits(res[1][0])) and np.array_equal(res[0][1], res[1][1])
+    big_off = np.array([0, 70000], np.int64)
+    tk = C.c_int32(-1)
+    o = g3d.TdfOutputs()
+    rc = L.g3d_tdf_batch_host_submit_u16(ctx, V.ctypes.data, big_off.ctypes.data, T.ctypes.data, np.array([0, 1], np.int64).ctypes.data, 1,
+                                         C.byref(p), C.byref(o), C.byref(tk))
+    assert rc == -1 and b"65,536" in L.g3d_last_error()
+    L.g3d_context_destroy(ctx)
