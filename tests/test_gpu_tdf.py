@@ -313,9 +313,12 @@ def test_cabi_error_paths(g3d):
     p.mode, p.ni = 0, 0
     assert L.g3d_tdf_batch(*args(need)) == -1
     p.ni = 32
-    # closest_tri shares its 32-bit word with 5 bits of sweep bookkeeping: 2^27 - 1 triangles are one too many
-    assert L.g3d_tdf_batch(v.data_ptr(), off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), (1 << 27) - 1, 1, C.byref(p),
+    # the evaluation queues carry global triangle numbers in 32 bits: 2^32 - 1 triangles in one call are one too many
+    # (the per-MESH limit of 2^27 - 2 is enforced on the device: G3D_MESH_TOO_MANY_TRIS)
+    assert L.g3d_tdf_batch(v.data_ptr(), off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), (1 << 32) - 1, 1, C.byref(p),
                            C.byref(o), ws.data_ptr(), need, None) == -1 and b"triangles" in L.g3d_last_error()
+    assert L.g3d_tdf_batch(v.data_ptr(), off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), (1 << 27) + 5, 1, C.byref(p),
+                           C.byref(o), ws.data_ptr(), need, None) == -3                       # accepted, but this workspace is too small
     assert L.g3d_tdf_batch(None, off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), 1, 1, C.byref(p), C.byref(o), ws.data_ptr(), need, None) == -1
     assert L.g3d_raycast_batch(None, None, 1, 64, 64, 525.0, 32.0, 32.0, 511, 32, None, None, None, None) == -1
     assert L.g3d_raycast_batch(v.data_ptr(), v.data_ptr(), 1, 4096, 4096, 525.0, 32.0, 32.0, 511, 32, sdf.data_ptr(), None, None, None) == -1
