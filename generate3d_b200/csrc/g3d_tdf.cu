@@ -1142,7 +1142,7 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
             }
             const float kappa = 1e-10f * S * S;
             // the cell index: CSR starts, entries in cell order, cell boxes
-            exact::exact_scan_kernel<<<(unsigned)n_mesh, 256, 0, stream>>>(w.cursor, w.cell_start, ncell);
+            exact::exact_scan_kernel<<<(unsigned)n_mesh, 1024, 0, stream>>>(w.cursor, w.cell_start, ncell);
             exact::exact_fill_kernel<<<(unsigned)((total_tris + 255) / 256), 256, 0, stream>>>(
                 w.tmp, tri_off, total_tris, n_mesh, ncell, w.cell_start, w.cursor, w.ent);
             exact::exact_cellbox_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, stream>>>(

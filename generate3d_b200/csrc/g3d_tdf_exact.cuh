@@ -218,33 +218,48 @@ __device__ __forceinline__ void index_triangle(const double* fp, const double* f
     tmp[t] = make_uint4(b.x, b.y, b.z, (uint32_t)cell);
 }
 
-// one CTA per mesh: counts -> exclusive starts; the counters become fill cursors (zero)
-__global__ void __launch_bounds__(256)
+// one CTA per mesh: counts -> exclusive starts, tile by tile with coalesced accesses (a 128^3 grid has 262,145 counts);
+// the counters become fill cursors (zero)
+__global__ void __launch_bounds__(1024)
 exact_scan_kernel(uint32_t* __restrict__ cursor, uint32_t* __restrict__ cell_start, int64_t ncell)
 {
-    __shared__ uint32_t s_sum[256];
-    const int mesh = blockIdx.x, tid = threadIdx.x;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int mesh = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t* cnt = cursor + (int64_t)mesh * (ncell + 1);
     uint32_t* st = cell_start + (int64_t)mesh * (ncell + 2);
-    const int64_t n = ncell + 1, per = (n + 255) / 256, lo = tid * per, hi = lo + per < n ? lo + per : n;
-    uint32_t sum = 0;
-    for (int64_t q = lo; q < hi; ++q) sum += cnt[q];
-    s_sum[tid] = sum;
+    const int64_t n = ncell + 1;
+    if (tid == 0) s_carry = 0u;
     __syncthreads();
-    for (int d = 1; d < 256; d <<= 1) {                          // Hillis-Steele inclusive scan of the 256 partial sums
-        uint32_t v = tid >= d ? s_sum[tid - d] : 0u;
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t q = base + tid;
+        const uint32_t v = q < n ? cnt[q] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane == 31) s_warp[wid] = incl;
         __syncthreads();
-        s_sum[tid] += v;
+        if (wid == 0) {
+            uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += up;
+            }
+            s_warp[lane] = wi - w;                               // exclusive offset of each warp inside the tile
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + s_warp[wid] + incl - v;
+        if (q < n) { st[q] = excl; cnt[q] = 0u; }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;                     // inclusive end of the tile
         __syncthreads();
     }
-    uint32_t run = s_sum[tid] - sum;
-    for (int64_t q = lo; q < hi; ++q) {
-        const uint32_t c = cnt[q];
-        st[q] = run;
-        cnt[q] = 0u;
-        run += c;
-    }
-    if (tid == 255) st[n] = s_sum[255];
+    if (tid == 0) st[n] = s_carry;
 }
 
 __global__ void __launch_bounds__(256)
