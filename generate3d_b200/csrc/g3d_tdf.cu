@@ -1148,14 +1148,24 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
             exact::exact_cellbox_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, stream>>>(
                 w.ent, tri_off, w.cell_start, ncell, n_groups, w.cellbox, w.occ);
             prof_mark(ST_ORDER, stream);
-            const int64_t want = (n_groups + exact::kExactWarps - 1) / exact::kExactWarps;
+            // voxel group per warp: 1x1x1 cells (8 voxels), 2x1x1 (16) or 2x2x1 (32); G3D_EXACT_GROUP overrides (tuning)
+            const char* e_grp = getenv("G3D_EXACT_GROUP");
+            const int grp = e_grp ? atoi(e_grp) : 32;
+            const int gcx = grp >= 16 ? 2 : 1, gcy = grp >= 32 ? 2 : 1;
+            const int ncx = exact::cells_of(p.ni), ncy = exact::cells_of(p.nj), ncz = exact::cells_of(p.nk);
+            const int64_t n_wgroups = (int64_t)n_mesh * ((ncx + gcx - 1) / gcx) * ((ncy + gcy - 1) / gcy) * ncz;
+            const int64_t want = (n_wgroups + exact::kExactWarps - 1) / exact::kExactWarps;
             const int64_t cap = (int64_t)sm_count() * 64;        // persistent warps: 16 CTAs per SM, 4 rounds of slack
             const char* e_occ = getenv("G3D_EXACT_OCC");        // tuning override: resident CTAs per SM the kernel is compiled for
-            const int occv = e_occ ? atoi(e_occ) : 8;          // measured on B200, 1,024 meshes: 8 CTAs per SM (64 registers) 22.9 ms, 6: 23.6, 5: 25.7
+            const int occv = e_occ ? atoi(e_occ) : 8;
             const unsigned nb = (unsigned)(want < cap ? want : cap);
-#define G3D_EXACT_LAUNCH(MINB) exact::tdf_exact3_kernel<MINB><<<nb, exact::kExactWarps * 32, 0, stream>>>( \
-                w.tri, w.fast, w.ent, w.cell_start, w.cellbox, w.occ, w.dil, tri_off, w.parity, w.key, p, R, far, kappa, n_groups, cnt)
-            if (occv >= 8) G3D_EXACT_LAUNCH(8); else if (occv >= 6) G3D_EXACT_LAUNCH(6); else if (occv <= 3) G3D_EXACT_LAUNCH(3); else G3D_EXACT_LAUNCH(5);
+#define G3D_EXACT_LAUNCH(MINB, CX, CY) exact::tdf_exact3_kernel<MINB, CX, CY, 1><<<nb, exact::kExactWarps * 32, 0, stream>>>( \
+                w.tri, w.fast, w.ent, w.cell_start, w.cellbox, w.occ, w.dil, tri_off, w.parity, w.key, p, R, far, kappa, n_wgroups, cnt)
+            // measured on B200, 1,024 meshes of 19,440 triangles, kernel time: 8 voxels per warp 21.7 ms, 16: 18.4, 32: 17.2 (at 8 CTAs
+            // per SM = 64 registers; 7: 17.7, 6: 18.7, 5: 19.3)
+            if (grp >= 32) { if (occv >= 8) G3D_EXACT_LAUNCH(8, 2, 2); else G3D_EXACT_LAUNCH(5, 2, 2); }
+            else if (grp >= 16) { if (occv >= 8) G3D_EXACT_LAUNCH(8, 2, 1); else G3D_EXACT_LAUNCH(5, 2, 1); }
+            else { if (occv >= 8) G3D_EXACT_LAUNCH(8, 1, 1); else G3D_EXACT_LAUNCH(5, 1, 1); }
 #undef G3D_EXACT_LAUNCH
             prof_mark(ST_EXACT, stream);
         }

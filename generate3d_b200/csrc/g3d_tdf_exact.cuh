@@ -305,60 +305,81 @@ exact_cellbox_kernel(const uint4* __restrict__ ent, const int64_t* __restrict__ 
                             pack_h2(__float2half_ru(hy), __float2half_ru(hz)), e - s);
 }
 
-// offset of the q-th cell of Chebyshev ring k >= 1 (24 k^2 + 2 cells): the two z faces, then the y faces without
-// their z edges, then the x faces without their y and z edges
+// offset (relative to the block's first cell) of the q-th cell of Chebyshev ring k around a block of CX x CY x CZ cells.
+// Ring 0 is the block itself; ring k >= 1 is the shell of the block grown by k cells: the two z faces, then the y faces
+// without their z edges, then the x faces without their y and z edges.
+template <int CX, int CY, int CZ>
+__device__ __forceinline__ int ring_size(int k)
+{
+    const int w = CX + 2 * k, h = CY + 2 * k, d = CZ + 2 * k;
+    return k == 0 ? CX * CY * CZ : w * h * d - (w - 2) * (h - 2) * (d - 2);
+}
+template <int CX, int CY, int CZ>
 __device__ __forceinline__ void ring_offset(int k, int q, int& dx, int& dy, int& dz)
 {
-    const int w = 2 * k + 1, u = 2 * k - 1, A = w * w, B = w * u, C = u * u;
+    if (k == 0) { dx = q % CX; dy = (q / CX) % CY; dz = q / (CX * CY); return; }
+    const int w = CX + 2 * k, h = CY + 2 * k, d = CZ + 2 * k, A = w * h, B = w * (d - 2), C = (h - 2) * (d - 2);
     if (q < 2 * A) {
         const int s = q >= A, r = q - s * A;
-        dz = s ? k : -k; dy = r / w - k; dx = r - (r / w) * w - k;
+        dz = s ? CZ - 1 + k : -k; dy = r / w - k; dx = r - (r / w) * w - k;
     } else if (q < 2 * A + 2 * B) {
         q -= 2 * A;
         const int s = q >= B, r = q - s * B;
-        dy = s ? k : -k; dz = r / w - (k - 1); dx = r - (r / w) * w - k;
+        dy = s ? CY - 1 + k : -k; dz = r / w - (k - 1); dx = r - (r / w) * w - k;
     } else {
         q -= 2 * A + 2 * B;
         const int s = q >= C, r = q - s * C;
-        dx = s ? k : -k; dz = r / u - (k - 1); dy = r - (r / u) * u - (k - 1);
+        dx = s ? CX - 1 + k : -k; dz = r / (h - 2) - (k - 1); dy = r - (r / (h - 2)) * (h - 2) - (k - 1);
     }
 }
 
 constexpr int kExactWarps = 4;            // warps per CTA
-constexpr int kRingTable = 124;           // rings 1 and 2 (26 + 98 cells) from a shared-memory table (+ the own cell)
 
-template <int MINB>
+// A warp owns a GROUP of CX x CY x CZ cells = NV = 8 CX CY CZ voxels (NV <= 32; lane = voxel wherever voxels are
+// enumerated). Bigger groups share the walk of the index and the entry tests between more voxels at the price of a
+// looser group bound (measured in tdf_solve's launcher).
+template <int MINB, int CX, int CY, int CZ>
 __global__ void __launch_bounds__(kExactWarps * 32, MINB)
 tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fast, const uint4* __restrict__ ent,
                   const uint32_t* __restrict__ cell_start, const uint4* __restrict__ cellbox, const uint32_t* __restrict__ occ,
                   const uint32_t* __restrict__ dil, const int64_t* __restrict__ tri_off, const uint32_t* __restrict__ parity,
                   u64* __restrict__ key, g3d_tdf_params P, float R, float far, float kappa, int64_t n_groups, u64* counter)
 {
+    constexpr int GX = kCell * CX, GY = kCell * CY, GZ = kCell * CZ, NV = GX * GY * GZ;
+    static_assert(NV <= 32, "a group is at most one voxel per lane");
+    constexpr int R1 = (CX + 2) * (CY + 2) * (CZ + 2) - CX * CY * CZ, R2 = (CX + 4) * (CY + 4) * (CZ + 4) - (CX + 2) * (CY + 2) * (CZ + 2);
+    constexpr int kRingTable = CX * CY * CZ + R1 + R2;     // rings 0..2 from a shared-memory table
+    static_assert((CY + 4) * (CZ + 4) <= 32 && CX + 4 <= 32, "the occupancy pre-test gives one (y, z) row of cells to a lane");
     // Two warp-private queues turn two uneven filters into dense work:
     //   pairs  (voxel, triangle) pairs that passed the per-voxel box test, waiting for stage 1 (32 at a time, one pair per lane)
     //   queue  pairs whose stage-1 interval reaches below the voxel's bound, waiting for stage 2 (32 at a time)
-    // The group's work is ONE loop -- pick the next list, take 32 entries, test each entry's box against the 8 voxels,
-    // run whichever stage has a full batch -- so that each stage exists once in the instruction stream (inlined at
+    // The group's work is ONE loop -- pick the next list, take 32 entries, test each entry's box against the group's
+    // voxels, run whichever stage has a full batch -- so that each stage exists once in the instruction stream (inlined at
     // every call site the kernel was twice the 32 KB instruction cache and mostly waited for instructions).
     __shared__ uint32_t s_pairs[kExactWarps][64];
     __shared__ uint32_t s_queue[kExactWarps][64];
-    __shared__ __align__(16) uint32_t s_ub[kExactWarps][8];   // per voxel of the group: float bits of ub2, the smallest a2 + e2 seen
-    __shared__ u64 s_best[kExactWarps][8];           // per voxel: float bits of the best faithful distance << 32 | its triangle
-    __shared__ int s_ring[kRingTable + 1];           // packed offsets (dx+8) | (dy+8)<<4 | (dz+8)<<8: own cell, rings 1 and 2
+    __shared__ uint32_t s_ub[kExactWarps][32];       // per voxel of the group: float bits of ub2, the smallest a2 + e2 seen
+    __shared__ __align__(16) float s_vb[kExactWarps][32];   // per voxel: the cull bound derived from ub2 (voxel units^2; -1 outside the grid)
+    __shared__ u64 s_best[kExactWarps][32];          // per voxel: float bits of the best faithful distance << 32 | its triangle
+    __shared__ int s_ring[kRingTable];               // packed offsets (dx+8) | (dy+8)<<4 | (dz+8)<<8 of rings 0, 1 and 2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    for (int q = threadIdx.x; q < kRingTable + 1; q += kExactWarps * 32) {
-        int dx = 0, dy = 0, dz = 0;
-        if (q >= 27) ring_offset(2, q - 27, dx, dy, dz); else if (q >= 1) ring_offset(1, q - 1, dx, dy, dz);
+    for (int q = threadIdx.x; q < kRingTable; q += kExactWarps * 32) {
+        int dx, dy, dz;
+        if (q >= CX * CY * CZ + R1) ring_offset<CX, CY, CZ>(2, q - CX * CY * CZ - R1, dx, dy, dz);
+        else if (q >= CX * CY * CZ) ring_offset<CX, CY, CZ>(1, q - CX * CY * CZ, dx, dy, dz);
+        else ring_offset<CX, CY, CZ>(0, q, dx, dy, dz);
         s_ring[q] = (dx + 8) | ((dy + 8) << 4) | ((dz + 8) << 8);
     }
     __syncthreads();
     uint32_t* pairs = s_pairs[warp];
     uint32_t* qu = s_queue[warp];
     volatile uint32_t* ubv = s_ub[warp];
+    volatile float* vbs = s_vb[warp];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int ncx = cells_of(ni), ncy = cells_of(nj), ncz = cells_of(nk);
-    const int64_t ncell = (int64_t)ncx * ncy * ncz, nvox = nvox_of(P), occ_words = (ncell + 31) / 32;
+    const int ngx = (ncx + CX - 1) / CX, ngy = (ncy + CY - 1) / CY, ngz = (ncz + CZ - 1) / CZ;
+    const int64_t ncell = (int64_t)ncx * ncy * ncz, ngroup = (int64_t)ngx * ngy * ngz, nvox = nvox_of(P), occ_words = (ncell + 31) / 32;
     const float inv_dx = 1.0f / P.dx;
     const float to_vox2 = inv_dx * inv_dx * 1.0001f * 1.001f;    // world distance^2 -> voxel units, rounded up, with the cull margin
     const float INF = __int_as_float(0x7f800000);
@@ -367,12 +388,13 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
 
     const int64_t wstride = (int64_t)gridDim.x * kExactWarps;
     for (int64_t g = (int64_t)blockIdx.x * kExactWarps + warp; g < n_groups; g += wstride) {
-        const int mesh = (int)(g / ncell);
-        const int64_t cg = g - (int64_t)mesh * ncell;
-        const int cx = (int)(cg % ncx), cy = (int)((cg / ncx) % ncy), cz = (int)(cg / ((int64_t)ncx * ncy));
-        // lanes 0..7 own the group's voxels (lane = voxel): validity, sign, start value, result
-        const int i = kCell * cx + (lane & 1), j = kCell * cy + ((lane >> 1) & 1), k = kCell * cz + ((lane >> 2) & 1);
-        const bool valid = lane < 8 && i < ni && j < nj && k < nk;
+        const int mesh = (int)(g / ngroup);
+        const int64_t cg = g - (int64_t)mesh * ngroup;
+        // first cell of the group's block of cells, first voxel of the group
+        const int cx = (int)(cg % ngx) * CX, cy = (int)((cg / ngx) % ngy) * CY, cz = (int)(cg / ((int64_t)ngx * ngy)) * CZ;
+        // lanes 0..NV-1 own the group's voxels (lane = voxel): validity, sign, start value, result
+        const int i = kCell * cx + lane % GX, j = kCell * cy + (lane / GX) % GY, k = kCell * cz + lane / (GX * GY);
+        const bool valid = lane < NV && i < ni && j < nj && k < nk;
         bool inside = false;
         if (valid) {                                    // running parity along i (makelevelset3.cpp:174-182)
             const uint32_t* par = parity + (int64_t)mesh * ((nvox + 31) / 32);
@@ -389,35 +411,28 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
         // like the reference's phi, the running minimum starts at `far` (makelevelset3.cpp:123): a triangle farther
         // away than that never registers. Outside voxels may stop at the truncation radius instead.
         const float start = inside ? far : fminf(R, far);
-        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-        if (vmask == 0u) continue;                      // cannot happen for cells inside the grid
+        if (!__any_sync(0xffffffffu, valid)) continue;  // cannot happen for groups inside the grid
         // stage 1 passes a pair to stage 2 iff a2 - e2 <= lim2 = 1.002 * ub2 + kappa, ub2 = smallest a2 + e2 seen (start^2 at first).
         // stage 2 keeps (distance, triangle) as one 64-bit key per voxel: atomicMin is "smaller distance, then lower index";
         // the initial key (start, 0) can only be beaten by a distance strictly below start, like the reference's d < phi.
         const u64 key0 = (u64)__float_as_uint(start) << 32;
         __syncwarp();
-        if (lane < 8) { ubv[lane] = __float_as_uint(start * start); s_best[warp][lane] = key0; }
-        __syncwarp();
-        // every lane keeps the 8 per-voxel cull bounds (voxel units^2; -1 for a voxel outside the grid) and their maximum
-        float vb[8], gb2;
+        ubv[lane] = __float_as_uint(start * start);
+        s_best[warp][lane] = key0;
+        // the per-voxel cull bounds (shared memory, one per lane's voxel) and their maximum over the group
+        float gb2;
         auto load_bounds = [&]() {
-            uint32_t u[8];
-            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
-                         : "r"((uint32_t)__cvta_generic_to_shared(&s_ub[warp][0])) : "memory");
-            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-                         : "r"((uint32_t)__cvta_generic_to_shared(&s_ub[warp][4])) : "memory");
-            gb2 = -1.f;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                vb[b] = ((vmask >> b) & 1u) ? fmaf(__uint_as_float(u[b]), 1.002f, kappa) * to_vox2 : -1.f;
-                gb2 = fmaxf(gb2, vb[b]);
-            }
+            const float b = valid ? fmaf(__uint_as_float(ubv[lane]), 1.002f, kappa) * to_vox2 : -1.f;
+            vbs[lane] = b;
+            gb2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(b, 0.f))));   // non-negative floats order like uints
+            __syncwarp();
         };
+        __syncwarp();
         load_bounds();
         const float x0 = (float)(kCell * cx), y0 = (float)(kCell * cy), z0 = (float)(kCell * cz);
         const float3 glo = make_float3(x0, y0, z0);
-        const float3 ghi = make_float3((float)min(kCell * cx + kCell - 1, ni - 1), (float)min(kCell * cy + kCell - 1, nj - 1),
-                                       (float)min(kCell * cz + kCell - 1, nk - 1));
+        const float3 ghi = make_float3((float)min(kCell * cx + GX - 1, ni - 1), (float)min(kCell * cy + GY - 1, nj - 1),
+                                       (float)min(kCell * cz + GZ - 1, nk - 1));
 
         const int64_t t0 = tri_off[mesh];
         const float4* Tm = tri + 4 * t0;
@@ -428,30 +443,29 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
         // a small triangle overhangs its home cell by at most D voxels (+ the outward rounding of the half-precision
         // boxes: one ulp at the grid's far end, 11 significant bits); ring k's cells are at least 2k - 2 voxels away
         const float D = __uint_as_float(__ldg(dil + mesh)) * 1.01f + 0.05f + (float)max(ni, max(nj, nk)) * (1.01f / 1024.f);
-        const int kmax = max(max(cx, ncx - 1 - cx), max(max(cy, ncy - 1 - cy), max(cz, ncz - 1 - cz)));
+        const int kmax = max(max(cx, ncx - cx - CX), max(max(cy, ncy - cy - CY), max(cz, ncz - cz - CZ)));
 
-        // anything at all nearby? the large list's length and the occupancy bits of the 5 x 5 x 5 cells around the group
-        // (one (y, z) row of cells per lane) decide whether rings 0..2 need a visit
+        // anything at all nearby? the large list's length and the occupancy bits of the cells of rings 0..2 (one (y, z) row of
+        // cells per lane) decide whether those rings need a visit
         uint32_t n_large = 0;
         bool near = false;
         {
             bool hit = false;
-            if (lane < 25) {
-                const int y = cy + lane % 5 - 2, z = cz + lane / 5 - 2;
+            if (lane < (CY + 4) * (CZ + 4)) {
+                const int y = cy + lane % (CY + 4) - 2, z = cz + lane / (CY + 4) - 2;
                 if (y >= 0 && z >= 0 && y < ncy && z < ncz) {
                     const uint32_t* OC = occ + (int64_t)mesh * occ_words;
-                    const int xs = max(cx - 2, 0), nb = min(cx + 2, ncx - 1) - xs + 1;
+                    const int xs = max(cx - 2, 0), nb = min(cx + CX + 1, ncx - 1) - xs + 1;
                     const int64_t b0 = xs + (int64_t)ncx * (y + (int64_t)ncy * z);
                     const int sh = (int)(b0 & 31);
                     uint32_t w = __ldg(OC + (b0 >> 5)) >> sh;
                     if (sh + nb > 32) w |= __ldg(OC + (b0 >> 5) + 1) << (32 - sh);
                     hit = (w & ((1u << nb) - 1u)) != 0u;
                 }
-            } else if (lane == 31) {
-                n_large = __ldg(CS + ncell + 1) - __ldg(CS + ncell);
             }
             near = __any_sync(0xffffffffu, hit);
-            n_large = __shfl_sync(0xffffffffu, n_large, 31);
+            if (lane == 0) n_large = __ldg(CS + ncell + 1) - __ldg(CS + ncell);
+            n_large = __shfl_sync(0xffffffffu, n_large, 0);
         }
 
         int pqn = 0, qn = 0;                             // fills of pairs / queue, warp-uniform
@@ -482,7 +496,7 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                     }
                     fresh = true;
                 } else if (state == ST_BATCH) {
-                    const int n = kr == 0 ? 1 : 24 * kr * kr + 2;
+                    const int n = ring_size<CX, CY, CZ>(kr);
                     if (q0 >= n) {
                         state = ST_RINGEND;
                     } else {
@@ -491,10 +505,10 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                         int dx = 0, dy = 0, dz = 0;
                         if (q < n) {
                             if (kr <= 2) {
-                                const int o = s_ring[(kr == 2 ? 27 : kr) + q];
+                                const int o = s_ring[(kr == 2 ? CX * CY * CZ + R1 : kr == 1 ? CX * CY * CZ : 0) + q];
                                 dx = (o & 15) - 8; dy = ((o >> 4) & 15) - 8; dz = ((o >> 8) & 15) - 8;
                             } else {
-                                ring_offset(kr, q, dx, dy, dz);
+                                ring_offset<CX, CY, CZ>(kr, q, dx, dy, dz);
                             }
                         }
                         const int ccx = cx + dx, ccy = cy + dy, ccz = cz + dz;
@@ -556,7 +570,7 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                 }
             }
             if (pos < total) {
-                // ---- the next 32 entries of the list: this lane's entry box against each of the 8 voxels with that voxel's bound
+                // ---- the next 32 entries of the list: this lane's entry box against each voxel of the group with that voxel's bound
                 const uint32_t q = pos + lane;
                 pos += 32;
                 // owner = the last lane whose exclusive offset is <= q (a lane with an empty list shares its successor's
@@ -577,23 +591,31 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                     tid = en.w;
                     ++n_tests;
                     const float2 a = unpack_h2(en.x), b = unpack_h2(en.y), c = unpack_h2(en.z);   // lo.x lo.y | lo.z hi.x | hi.y hi.z
-                    // squared gap per axis for the two node coordinates of the group on that axis
-                    float ex[2], ey[2], ez[2];
+                    // squared gap per axis for each node coordinate of the group on that axis
+                    float ex[GX], ey[GY], ez[GZ];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float gx = x0 + (float)h, gy = y0 + (float)h, gz = z0 + (float)h;
-                        const float tx = fmaxf(0.f, fmaxf(a.x - gx, gx - b.y));
-                        const float ty = fmaxf(0.f, fmaxf(a.y - gy, gy - c.x));
-                        const float tz = fmaxf(0.f, fmaxf(b.x - gz, gz - c.y));
-                        ex[h] = tx * tx; ey[h] = ty * ty; ez[h] = tz * tz;
+                    for (int h = 0; h < GX; ++h) { const float gx = x0 + (float)h, t = fmaxf(0.f, fmaxf(a.x - gx, gx - b.y)); ex[h] = t * t; }
+#pragma unroll
+                    for (int h = 0; h < GY; ++h) { const float gy = y0 + (float)h, t = fmaxf(0.f, fmaxf(a.y - gy, gy - c.x)); ey[h] = t * t; }
+#pragma unroll
+                    for (int h = 0; h < GZ; ++h) { const float gz = z0 + (float)h, t = fmaxf(0.f, fmaxf(b.x - gz, gz - c.y)); ez[h] = t * t; }
+                    // (x, y) partial sums once, the voxels' bounds four at a time
+                    float exy[GX * GY];
+#pragma unroll
+                    for (int h = 0; h < GX * GY; ++h) exy[h] = ex[h % GX] + ey[h / GX];
+#pragma unroll
+                    for (int v4 = 0; v4 < NV; v4 += 4) {
+                        float b4[4];
+                        asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4[0]), "=f"(b4[1]), "=f"(b4[2]), "=f"(b4[3])
+                                     : "r"((uint32_t)__cvta_generic_to_shared(&s_vb[warp][v4])) : "memory");
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (exy[(v4 + u) % (GX * GY)] + ez[(v4 + u) / (GX * GY)] <= b4[u]) vm |= 1u << (v4 + u);
                     }
-#pragma unroll
-                    for (int vx = 0; vx < 8; ++vx)
-                        if (ex[vx & 1] + ey[(vx >> 1) & 1] + ez[vx >> 2] <= vb[vx]) vm |= 1u << vx;
                 }
             }
             // ---- pairs of this batch to the queue, voxel by voxel; whichever stage has a full batch (or anything at all when
-            // draining, in the extra round vx == 8) runs, the later stage first so that no queue overflows; each stage exists once
+            // draining, after the last voxel) runs, the later stage first so that no queue overflows; each stage exists once
             uint32_t um = __reduce_or_sync(0xffffffffu, vm);          // voxels that got at least one pair from this batch
             if (!drain && um == 0u) continue;
             for (;;) {
@@ -602,7 +624,7 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                     um &= um - 1u;
                     const bool mine = (vm >> vx) & 1u;
                     const uint32_t m = __ballot_sync(0xffffffffu, mine);
-                    if (mine) pairs[pqn + __popc(m & lt)] = (tid << 3) | (uint32_t)vx;
+                    if (mine) pairs[pqn + __popc(m & lt)] = (tid << 5) | (uint32_t)vx;
                     pqn += __popc(m);
                 }
                 const bool last = um == 0u && drain;
@@ -619,11 +641,11 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                         uint32_t pr = 0;
                         if (lane < c) {
                             pr = pairs[pqn + lane];
-                            const int o = pr & 7u;
-                            const V3 go = node_pos(kCell * cx + (o & 1), kCell * cy + ((o >> 1) & 1), kCell * cz + (o >> 2), P);
+                            const int o = pr & 31u;
+                            const V3 go = node_pos(kCell * cx + o % GX, kCell * cy + (o / GX) % GY, kCell * cz + o / (GX * GY), P);
                             bool flagged;
                             float e2;
-                            const float a2 = fast_dist2(go, Fm + 5 * (int64_t)(pr >> 3), flagged, e2);
+                            const float a2 = fast_dist2(go, Fm + 5 * (int64_t)(pr >> 5), flagged, e2);
                             ++n_pairs;
                             const float ub = __uint_as_float(ubv[o]);
                             cand = flagged || !(a2 - e2 > fmaf(ub, 1.002f, kappa));
@@ -638,16 +660,14 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                         // stage 2 on up to 32 queued pairs: the bit-faithful function decides
                         const int c = min(qn, 32);
                         qn -= c;
-                        uint32_t e = 0;
-                        float d = INF;
                         if (lane < c) {
-                            e = qu[qn + lane];
-                            const int o = e & 7u;
-                            const V3 go = node_pos(kCell * cx + (o & 1), kCell * cy + ((o >> 1) & 1), kCell * cz + (o >> 2), P);
-                            d = point_triangle_distance(go, load_trirec(Tm + 4 * (int64_t)(e >> 3)));
+                            const uint32_t e = qu[qn + lane];
+                            const int o = e & 31u;
+                            const V3 go = node_pos(kCell * cx + o % GX, kCell * cy + (o / GX) % GY, kCell * cz + o / (GX * GY), P);
+                            const float d = point_triangle_distance(go, load_trirec(Tm + 4 * (int64_t)(e >> 5)));
                             ++n_faithful;
+                            atomicMin(&s_best[warp][o], ((u64)__float_as_uint(d) << 32) | (e >> 5));
                         }
-                        if (lane < c) atomicMin(&s_best[warp][e & 7u], ((u64)__float_as_uint(d) << 32) | (e >> 3));
                     }
                 }
                 if (um == 0u) break;

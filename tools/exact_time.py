@@ -17,4 +17,4 @@ for rep in range(4):
     dfgen.tdf_batch(dV, dvo, dT, dto, mode="exact", outputs=outs, out=o)
     _lib.check(L.g3d_profile_read(sm, None))
 st = np.frombuffer(sm, np.float32)
-print("G3D_EXACT_OCC=%s  prep %.2f index %.2f exact %.2f finalize %.2f ms" % (os.environ.get("G3D_EXACT_OCC"), st[1], st[3], st[6], st[5]), flush=True)
+print("G3D_EXACT_GROUP=%s G3D_EXACT_OCC=%s  prep %.2f index %.2f exact %.2f finalize %.2f ms" % (os.environ.get("G3D_EXACT_GROUP"), os.environ.get("G3D_EXACT_OCC"), st[1], st[3], st[6], st[5]), flush=True)
