@@ -482,15 +482,19 @@ tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ b
             const float eyz2 = fmaf(ey, ey, ez * ez);
             const int e = (i0 - I0) + kTile * ((j - J0) + kTile * (k - K0));
             const uint32_t pos = (uint32_t)i0 | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+            // the row's nodes that survive the cull as a bit mask per lane; only the positions at which some lane has a
+            // survivor go through the (warp-wide) compaction
+            uint32_t pm = 0;
 #pragma unroll
             for (int a = 0; a < kLaneI; ++a) {
-                if (a >= bimax) break;
-                bool pass = false;
                 if (rv && a < bi) {
                     const float cur = __uint_as_float(s_w[2 * (e + a) + 1]);
-                    pass = !(ex2[a] + eyz2 > fmaf(cur * cur, 1.001f, 1e-12f));
+                    if (!(ex2[a] + eyz2 > fmaf(cur * cur, 1.001f, 1e-12f))) pm |= 1u << a;
                 }
-                push(pass, (uint32_t)t, pos + (uint32_t)a);
+            }
+            for (uint32_t um = __reduce_or_sync(0xffffffffu, pm); um; um &= um - 1u) {
+                const int a = __ffs(um) - 1;
+                push((pm >> a) & 1u, (uint32_t)t, pos + (uint32_t)a);
             }
             if (++j > j1) { j = j0; ++k; }
         }

@@ -614,21 +614,25 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                     }
                 }
             }
-            // ---- pairs of this batch to the queue, voxel by voxel; whichever stage has a full batch (or anything at all when
-            // draining, after the last voxel) runs, the later stage first so that no queue overflows; each stage exists once
-            uint32_t um = __reduce_or_sync(0xffffffffu, vm);          // voxels that got at least one pair from this batch
-            if (!drain && um == 0u) continue;
+            // ---- pairs of this batch to the queue, one pair per lane and round (a lane's lowest remaining voxel); whichever
+            // stage has a full batch (or anything at all when draining, after the last round) runs, the later stage first so
+            // that no queue overflows; each stage exists once
+            bool um = __any_sync(0xffffffffu, vm != 0u);
+            if (!drain && !um) continue;
             for (;;) {
                 if (um) {
-                    const int vx = __ffs(um) - 1;
-                    um &= um - 1u;
-                    const bool mine = (vm >> vx) & 1u;
+                    const bool mine = vm != 0u;
                     const uint32_t m = __ballot_sync(0xffffffffu, mine);
-                    if (mine) pairs[pqn + __popc(m & lt)] = (tid << 5) | (uint32_t)vx;
+                    if (mine) {
+                        const int vx = __ffs(vm) - 1;
+                        vm &= vm - 1u;
+                        pairs[pqn + __popc(m & lt)] = (tid << 5) | (uint32_t)vx;
+                    }
                     pqn += __popc(m);
+                    um = __any_sync(0xffffffffu, vm != 0u);
                 }
-                const bool last = um == 0u && drain;
-                if (pqn < 32 && !last) { if (um == 0u) break; continue; }
+                const bool last = !um && drain;
+                if (pqn < 32 && !last) { if (!um) break; continue; }
                 for (;;) {
                     const int act = qn >= 32 ? 2 : pqn >= 32 ? 1 : !last ? 0 : pqn > 0 ? 1 : (final && qn > 0) ? 2 : 0;
                     if (act == 0) break;
@@ -637,20 +641,22 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                         // stage 1 on up to 32 (voxel, triangle) pairs, one pair per lane
                         const int c = min(pqn, 32);
                         pqn -= c;
-                        bool cand = false;
+                        bool cand = false, flagged = false;
                         uint32_t pr = 0;
+                        float lo2 = 0.f;
+                        int o = 0;
                         if (lane < c) {
                             pr = pairs[pqn + lane];
-                            const int o = pr & 31u;
+                            o = pr & 31u;
                             const V3 go = node_pos(kCell * cx + o % GX, kCell * cy + (o / GX) % GY, kCell * cz + o / (GX * GY), P);
-                            bool flagged;
                             float e2;
                             const float a2 = fast_dist2(go, Fm + 5 * (int64_t)(pr >> 5), flagged, e2);
                             ++n_pairs;
-                            const float ub = __uint_as_float(ubv[o]);
-                            cand = flagged || !(a2 - e2 > fmaf(ub, 1.002f, kappa));
-                            if (!flagged && a2 + e2 < ub) atomicMin(&s_ub[warp][o], __float_as_uint(a2 + e2));   // non-negative floats order like uints
+                            lo2 = a2 - e2;
+                            if (!flagged && a2 + e2 < __uint_as_float(ubv[o])) atomicMin(&s_ub[warp][o], __float_as_uint(a2 + e2));   // non-negative floats order like uints
                         }
+                        __syncwarp();                    // the batch's own upper bounds already count for its filter
+                        if (lane < c) cand = flagged || !(lo2 > fmaf(__uint_as_float(ubv[o]), 1.002f, kappa));
                         const uint32_t cm = __ballot_sync(0xffffffffu, cand);
                         if (cand) qu[qn + __popc(cm & lt)] = pr;
                         qn += __popc(cm);
@@ -670,7 +676,7 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
                         }
                     }
                 }
-                if (um == 0u) break;
+                if (!um) break;
             }
         }
         __syncwarp();

@@ -179,3 +179,56 @@ def test_vox2mesh_txt_and_ply(g3d, oracle, tmp_path, unitless):
         dfgen.vox2mesh(str(df), str(tmp_path / "noext"))
     with pytest.raises(g3d.G3DError):
         dfgen.vox2mesh(str(df), str(ply), cmap="magma")
+
+
+def test_vox2mesh_pdf_block_and_redcenter(g3d, oracle, tmp_path):
+    """A .df with a trailing pdf block (LoaderVOX.h:38-41) colours each visible voxel with jet(pdf) (Colormap.h:1301-1325,
+    T = float with the header's double-typed literals); --redcenter marks the central 3x3x3 block when there is no pdf
+    block (vox2mesh/main.cpp:180-192). Checked against a numpy restatement (Colormap.h needs Eigen: unpinned)."""
+    from generate3d_b200 import dfgen
+    rng = np.random.default_rng(9)
+    dim = 8
+    sdf = rng.uniform(-3, 3, (dim, dim, dim)).astype(np.float32)
+    pdf = rng.uniform(-0.5, 1.5, (dim, dim, dim)).astype(np.float32)
+    g2w = np.eye(4, dtype=np.float32).reshape(-1)
+
+    def jet(v):
+        v = np.float32(v)
+        vmin, vmax = np.float32(-0.2), np.float32(1.0)
+        v = min(max(v, vmin), vmax)
+        dv = np.float32(vmax - vmin)
+        c = [np.float32(1), np.float32(1), np.float32(1)]
+        if float(v) < float(vmin) + 0.25 * float(dv):
+            c[0] = np.float32(0)
+            c[1] = np.float32(np.float32(np.float32(4) * np.float32(v - vmin)) / dv)
+        elif float(v) < float(vmin) + 0.5 * float(dv):
+            c[0] = np.float32(0)
+            c[2] = np.float32(1 + 4 * (float(vmin) + 0.25 * float(dv) - float(v)) / float(dv))
+        elif float(v) < float(vmin) + 0.75 * float(dv):
+            c[0] = np.float32(4 * (float(v) - float(vmin) - 0.5 * float(dv)) / float(dv))
+            c[2] = np.float32(0)
+        else:
+            c[1] = np.float32(1 + 4 * (float(vmin) + 0.75 * float(dv) - float(v)) / float(dv))
+            c[2] = np.float32(0)
+        return [int(np.float32(255.0) * x) for x in c]
+
+    df = tmp_path / "p.df"
+    with open(df, "wb") as f:
+        f.write(np.int32([dim, dim, dim]).tobytes() + np.float32(1).tobytes() + g2w.tobytes() + sdf.tobytes() + pdf.tobytes())
+    dfgen.vox2mesh(str(df), str(tmp_path / "p.ply"), write_ply=False)
+    rows = (tmp_path / "p.txt").read_text().splitlines()
+    want = []
+    for k in range(dim):
+        for j in range(dim):
+            for i in range(dim):
+                if abs(sdf[k, j, i]) <= 1.0:
+                    want.append("%d %d %d %d %d %d" % (i, j, k, *jet(pdf[k, j, i])))
+    assert rows == want and len(rows) > 50
+    # no pdf block + --redcenter: pdf = 1 in the central block (index i*dim*dim + j*dim + k, as the reference writes it)
+    with open(df, "wb") as f:
+        f.write(np.int32([dim, dim, dim]).tobytes() + np.float32(1).tobytes() + g2w.tobytes() + np.zeros_like(sdf).tobytes())
+    dfgen.vox2mesh(str(df), str(tmp_path / "p.ply"), redcenter=True, write_ply=False)
+    rows = (tmp_path / "p.txt").read_text().splitlines()
+    assert len(rows) == dim ** 3
+    red = [r for r in rows if r.endswith(" %d %d %d" % tuple(jet(1.0)))]
+    assert len(red) == 27 and rows[0].endswith(" 0 169 255")

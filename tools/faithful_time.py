@@ -1,5 +1,4 @@
-"""Step time of faithful mode on the configs[2] batch (tuning aid): python tools/faithful_time.py [meshes]
-Environment: G3D_TDF_PIPE (slices of the init/sweep pipeline; 1 = serial kernels)."""
+"""Step time of faithful mode on the configs[2] batch (tuning aid): python tools/faithful_time.py [meshes]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,20 +9,14 @@ V, voff, T, toff = S.table_batch(M, 18, 0)
 dV, dT = torch.from_numpy(V).cuda(), torch.from_numpy(T.view(np.int32)).cuda()
 dvo, dto = torch.from_numpy(voff).cuda(), torch.from_numpy(toff).cuda()
 outs = ("sdf", "tdf", "tdflog", "occ_bits", "status")
-ref = None
-for pipe in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "2", "4", "8"]):
-    os.environ["G3D_TDF_PIPE"] = pipe
-    o = dfgen.tdf_batch(dV, dvo, dT, dto, outputs=outs)
-    for _ in range(3):
-        dfgen.tdf_batch(dV, dvo, dT, dto, outputs=outs, out=o)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10):
-        dfgen.tdf_batch(dV, dvo, dT, dto, outputs=outs, out=o)
-    b.record()
-    torch.cuda.synchronize()
-    same = True if ref is None else bool(torch.equal(ref, o["sdf"]))
-    if ref is None:
-        ref = o["sdf"].clone()
-    print("G3D_TDF_PIPE=%s  %.2f ms/step  same=%s" % (pipe, a.elapsed_time(b) / 10, same), flush=True)
+o = dfgen.tdf_batch(dV, dvo, dT, dto, outputs=outs)
+for _ in range(3):
+    dfgen.tdf_batch(dV, dvo, dT, dto, outputs=outs, out=o)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    dfgen.tdf_batch(dV, dvo, dT, dto, outputs=outs, out=o)
+b.record()
+torch.cuda.synchronize()
+print("faithful, %d meshes: %.2f ms/step" % (M, a.elapsed_time(b) / 10), flush=True)
