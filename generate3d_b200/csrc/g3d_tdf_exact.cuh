@@ -388,10 +388,22 @@ tdf_exact3_kernel(const float4* __restrict__ tri, const float4* __restrict__ fas
 
     const int64_t wstride = (int64_t)gridDim.x * kExactWarps;
     for (int64_t g = (int64_t)blockIdx.x * kExactWarps + warp; g < n_groups; g += wstride) {
-        const int mesh = (int)(g / ngroup);
-        const int64_t cg = g - (int64_t)mesh * ngroup;
-        // first cell of the group's block of cells, first voxel of the group
-        const int cx = (int)(cg % ngx) * CX, cy = (int)((cg / ngx) % ngy) * CY, cz = (int)(cg / ((int64_t)ngx * ngy)) * CZ;
+        // (32-bit divisions whenever the numbers allow: a 64-bit division is ~100 instructions, and there were five per group)
+        int mesh, cx, cy, cz;
+        if (n_groups < 0x7fffffffll) {
+            const uint32_t g32 = (uint32_t)g, ng32 = (uint32_t)ngroup;
+            mesh = (int)(g32 / ng32);
+            const uint32_t cg = g32 - (uint32_t)mesh * ng32, row = cg / (uint32_t)ngx;
+            cx = (int)(cg - row * (uint32_t)ngx) * CX;
+            cz = (int)(row / (uint32_t)ngy);
+            cy = (int)(row - (uint32_t)cz * (uint32_t)ngy) * CY;
+            cz *= CZ;
+        } else {
+            mesh = (int)(g / ngroup);
+            const int64_t cg = g - (int64_t)mesh * ngroup;
+            cx = (int)(cg % ngx) * CX; cy = (int)((cg / ngx) % ngy) * CY; cz = (int)(cg / ((int64_t)ngx * ngy)) * CZ;
+        }
+        // (cx, cy, cz): first cell of the group's block of cells; the group's first voxel is kCell times that
         // lanes 0..NV-1 own the group's voxels (lane = voxel): validity, sign, start value, result
         const int i = kCell * cx + lane % GX, j = kCell * cy + (lane / GX) % GY, k = kCell * cz + lane / (GX * GY);
         const bool valid = lane < NV && i < ni && j < nj && k < nk;
