@@ -670,7 +670,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     // s_thr[s][r][cls]: code of the last sweep before s in which a node of boundary class cls examined the
     // neighbour that slot r of sweep s points at (-1: never). cls = cx + 3*cy + 9*cz, c = 0 at coordinate 0,
     // 2 at coordinate n-1, 1 in between: a node on a grid face is not part of every sweep's lattice.
-    __shared__ int8_t s_thr[16][7][27];
+    __shared__ __align__(8) int8_t s_thr[16][27][8];   // [s][cls][r] (r = 7: padding): a node fetches its seven thresholds in one load
     __shared__ int s_tmin[16];                      // smallest s_thr over the slots and the classes present in sweep s
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -680,10 +680,14 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     // q_pos[e] is replaced by the pair's result (by the lane that read it). Shared memory is worth saving here:
     // what the CTAs of an SM do not take stays L1 (measured, 1,024 meshes: flat up to a 164 KB carve-out with the
     // bricked keys, +9 % at 196 KB, +100 % with the L1 squeezed to its minimum).
-    // s_dirty[d][L]: newest change code among the upwind neighbours of the nodes of level L in direction d
-    uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev]
+    // s_dirty[d][l + 3]: newest change code among the nodes whose own level in direction d is l (-3 <= l < nlev; nodes on
+    // the grid faces lie outside some sweep lattices). A node of level l is upwind of nodes of levels l+1 .. l+3, so level
+    // L has nothing new upwind when the three entries below it are old: one store per direction and change, three loads
+    // per level.
+    const int dstride = nlev + 3;
+    uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev + 3]
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
-    for (int l = threadIdx.x; l < 8 * nlev; l += NT) s_dirty[l] = 0;
+    for (int l = threadIdx.x; l < 8 * dstride; l += NT) s_dirty[l] = 0;
     for (int e = threadIdx.x; e < 16 * 7 * 27; e += NT) {
         const int cls = e % 27, r = (e / 27) % 7, s = e / (27 * 7), a = r + 1;
         const int c3[3] = { cls % 3, (cls / 3) % 3, cls / 9 };
@@ -699,7 +703,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
             }
             if (ok) thr = sp + 1;
         }
-        s_thr[s][r][cls] = (int8_t)thr;
+        s_thr[s][cls][r] = (int8_t)thr;
     }
     __syncthreads();
     if (threadIdx.x < 16) {
@@ -712,7 +716,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
             for (int ax = 0; ax < 3; ++ax)
                 if (d[ax] > 0 ? c3[ax] == 0 : c3[ax] == 2) present = false;
             if (present)
-                for (int r = 0; r < 7; ++r) m = min(m, (int)s_thr[s][r][cls]);
+                for (int r = 0; r < 7; ++r) m = min(m, (int)s_thr[s][cls][r]);
         }
         s_tmin[s] = m;
     }
@@ -731,11 +735,11 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
         int di, dj, dk;
         sweep_dir(s, di, dj, dk);
         const int tmin = s_tmin[s];
-        const uint8_t* dirty = s_dirty + (s & 7) * nlev;
+        const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
         for (int L = 0; L < nlev; ++L) {
             // nothing upwind of this whole level has changed since it was last examined: every comparison the
             // reference would make here is known to fail. (Cluster variant: the table is per CTA, no skipping.)
-            if (!CL && (int)dirty[L] <= tmin) continue;
+            if (!CL && max(max((int)dirty[L], (int)dirty[L + 1]), (int)dirty[L + 2]) <= tmin) continue;
             const int beg = s_lev[L], end = s_lev[L + 1];
             // node phase of one round: candidates of this lane's node go to the queue from slot `qbase` on; returns
             // the number of pairs the warp queued (warp-uniform)
@@ -757,13 +761,16 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                               n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
                     const int cls = (i == 0 ? 0 : (i == ni - 1 ? 2 : 1)) + 3 * (j == 0 ? 0 : (j == nj - 1 ? 2 : 1)) +
                                     9 * (k == 0 ? 0 : (k == nk - 1 ? 2 : 1));
-                    const int8_t* th = &s_thr[s][0][cls];
+                    const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][cls][0]);   // bytes 0..3 | 4..6
                     const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
                                    w5 = Klo[2 * n5], w6 = Klo[2 * n6];
-#define G3D_CAND(w, off) (((int)((w) >> 27) > th[off] && ((w) & kTriMask) != kTriMask) ? (int)((w) & kTriMask) : -1)
-                    c0 = G3D_CAND(w0, 0); c1 = G3D_CAND(w1, 27); c2 = G3D_CAND(w2, 54); c3 = G3D_CAND(w3, 81);
-                    c4 = G3D_CAND(w4, 108); c5 = G3D_CAND(w5, 135); c6 = G3D_CAND(w6, 162);
+#define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
+#define G3D_CAND(w, thr) (((int)((w) >> 27) > (thr) && ((w) & kTriMask) != kTriMask) ? (int)((w) & kTriMask) : -1)
+                    c0 = G3D_CAND(w0, G3D_THR(thw.x, 0)); c1 = G3D_CAND(w1, G3D_THR(thw.x, 1)); c2 = G3D_CAND(w2, G3D_THR(thw.x, 2));
+                    c3 = G3D_CAND(w3, G3D_THR(thw.x, 3)); c4 = G3D_CAND(w4, G3D_THR(thw.y, 0)); c5 = G3D_CAND(w5, G3D_THR(thw.y, 1));
+                    c6 = G3D_CAND(w6, G3D_THR(thw.y, 2));
 #undef G3D_CAND
+#undef G3D_THR
                     if ((c0 & c1 & c2 & c3 & c4 & c5 & c6) >= 0) {      // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
                         phi = __uint_as_float((uint32_t)(kv >> 32));
@@ -809,8 +816,8 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     const uint8_t code = (uint8_t)(s + 1);
                     K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)code << 27) | (uint32_t)ct;
                     if (!CL) {
-                        // in every direction d this node is upwind of nodes 1..3 levels further on: stamp those
-                        // levels (codes only grow and all writers of a sweep write the same value)
+                        // stamp the node's own level in every direction (codes only grow and all writers of a sweep
+                        // write the same value)
                         const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
 #pragma unroll
                         for (int dq = 0; dq < 8; ++dq) {
@@ -818,12 +825,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                             sweep_dir(dq, ei, ej, ek);
                             const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) +
                                            (ek > 0 ? pk - 1 : nk - 2 - pk);
-                            uint8_t* row = s_dirty + dq * nlev;
-#pragma unroll
-                            for (int up = 1; up <= 3; ++up) {
-                                const int l = lv + up;
-                                if (l >= 0 && l < nlev) row[l] = code;
-                            }
+                            s_dirty[dq * dstride + lv + 3] = code;
                         }
                     }
                 }
@@ -958,7 +960,7 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
                     u64* cnt, cudaStream_t stream)
 {
     const int lev_words = (nlev + 1 + 3) & ~3;
-    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue) * 4 + (size_t)8 * nlev;
+    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue) * 4 + (size_t)8 * (nlev + 3);
     auto kern = tdf_sweep_kernel<NT, CL>;
     G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
