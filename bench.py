@@ -180,6 +180,8 @@ def cpu_raycast_port(depth, poses, focal):
 def cpu_raycast_loop(depth, pose, focal):
     """One view through the cost-faithful port of the reference's raycast_depth (its 32,768-iteration Python loop)."""
     from oracle import oracle as O
+    import torch                                         # noqa: F401 -- loaded before the clock starts, like a running script has it
+    torch.zeros(1).float()
     t0 = time.perf_counter()
     O.raycast_depth_reference_loop(depth, pose, focal)
     return time.perf_counter() - t0

@@ -1156,10 +1156,15 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
                 w.ent, tri_off, w.cell_start, ncell, n_groups, w.cellbox, w.occ);
             prof_mark(ST_ORDER, stream);
             // voxel group per warp: 1x1x1 cells (8 voxels), 2x1x1 (16) or 2x2x1 (32); G3D_EXACT_GROUP overrides (tuning)
+            // the largest group that still gives the GPU two waves of warps (a single 32^3 mesh has only 1,024 groups of 32 voxels)
             const char* e_grp = getenv("G3D_EXACT_GROUP");
-            const int grp = e_grp ? atoi(e_grp) : 32;
-            const int gcx = grp >= 16 ? 2 : 1, gcy = grp >= 32 ? 2 : 1;
             const int ncx = exact::cells_of(p.ni), ncy = exact::cells_of(p.nj), ncz = exact::cells_of(p.nk);
+            const int64_t enough = (int64_t)sm_count() * 64;
+            int grp = 32;
+            if ((int64_t)n_mesh * ((ncx + 1) / 2) * ((ncy + 1) / 2) * ncz < enough) grp = 16;
+            if (grp == 16 && (int64_t)n_mesh * ((ncx + 1) / 2) * ncy * ncz < enough) grp = 8;
+            if (e_grp) grp = atoi(e_grp);
+            const int gcx = grp >= 16 ? 2 : 1, gcy = grp >= 32 ? 2 : 1;
             const int64_t n_wgroups = (int64_t)n_mesh * ((ncx + gcx - 1) / gcx) * ((ncy + gcy - 1) / gcy) * ncz;
             const int64_t want = (n_wgroups + exact::kExactWarps - 1) / exact::kExactWarps;
             const int64_t cap = (int64_t)sm_count() * 64;        // persistent warps: 16 CTAs per SM, 4 rounds of slack
