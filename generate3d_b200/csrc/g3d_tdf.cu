@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 #include <limits.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "g3d_internal.h"
 #include "g3d_ptd.cuh"
@@ -53,8 +54,18 @@ struct TdfWs {
     uint32_t* parity;
     uint32_t* order;        // packed a | b<<10 | c<<20, grouped by level
     int32_t*  level_start;  // [nlev + 1]
+    uint32_t* chg;          // [n_mesh][17][act_words]: nodes changed under each code (sweep activity bitmaps), small grids only
+    uint32_t* bnd;          // [act_words]: nodes on a grid face
+    int       act_words;    // 0: the grid is too large for the sweep's activity bitmap
     size_t    bytes;
 };
+
+// the sweep keeps one bit per grid node in shared memory when that is at most 8 KB
+inline int act_words_of(const g3d_tdf_params& p)
+{
+    const int64_t nvox = (int64_t)p.ni * p.nj * p.nk;
+    return nvox <= 65536 ? (int)((nvox + 31) / 32) : 0;
+}
 
 __host__ __device__ inline int64_t nvox_of(const g3d_tdf_params& p) { return (int64_t)p.ni * p.nj * p.nk; }
 
@@ -94,6 +105,9 @@ TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
     w.order = (uint32_t*)take((size_t)nsweep * 4);
     w.level_start = (int32_t*)take((size_t)(nlev_of(p) + 2) * 4);
+    w.act_words = act_words_of(p);
+    w.chg = (uint32_t*)take((size_t)n_mesh * 17 * w.act_words * 4);
+    w.bnd = (uint32_t*)take((size_t)w.act_words * 4);
     w.bytes = off;
     return w;
 }
@@ -581,8 +595,18 @@ tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ b
 // ----------------------------------------------------------- sweep order ----
 // Nodes of the sweep lattice (ni-1)(nj-1)(nk-1) grouped by level a+b+c.
 __global__ void __launch_bounds__(1024)
-tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order, int32_t* __restrict__ level_start)
+tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order, int32_t* __restrict__ level_start,
+                 uint32_t* __restrict__ bnd, int act_words)
 {
+    // (the grid is (na+1) x (nb+1) x (nc+1) nodes) bit i + ni (j + nj k) of bnd: the node lies on a grid face
+    for (int w = threadIdx.x; w < act_words; w += blockDim.x) {
+        uint32_t m = 0u;
+        for (int b = 0; b < 32; ++b) {
+            const int p = 32 * w + b, i = p % (na + 1), r = p / (na + 1), j = r % (nb + 1), k = r / (nb + 1);
+            if (k <= nc && (i == 0 || i == na || j == 0 || j == nb || k == 0 || k == nc)) m |= 1u << b;
+        }
+        bnd[w] = m;
+    }
     // Closed form, no atomics: within a level nodes are sorted by (c, b). Neighbouring lanes of a sweep warp then
     // hold neighbouring grid rows, whose upwind rows coincide, so a warp's loads fall into few cache lines -- and
     // the order is the same on every run.
@@ -663,15 +687,15 @@ template <int NT, bool CL>
 __global__ void __launch_bounds__(NT)
 tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                  const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
-                 int lev_words, g3d_tdf_params P, u64* counter)
+                 int lev_words, g3d_tdf_params P, u64* counter, int s_begin, int s_end, uint32_t* chg, int act_words)
 {
     u64 n_eval = 0;
     extern __shared__ uint32_t s_mem[];
-    // s_thr[s][r][cls]: code of the last sweep before s in which a node of boundary class cls examined the
-    // neighbour that slot r of sweep s points at (-1: never). cls = cx + 3*cy + 9*cz, c = 0 at coordinate 0,
-    // 2 at coordinate n-1, 1 in between: a node on a grid face is not part of every sweep's lattice.
-    __shared__ __align__(8) int8_t s_thr[16][27][8];   // [s][cls][r] (r = 7: padding): a node fetches its seven thresholds in one load
-    __shared__ int s_tmin[16];                      // smallest s_thr over the slots and the classes present in sweep s
+    // s_thr[s][f][r]: code of the last sweep before s in which a node examined the neighbour that slot r of sweep s points
+    // at (-1: never). f = the axes on which the node lies on a grid face (bit 0: x ...): such a node is only part of the
+    // sweeps that run towards its face, so for it an earlier sweep counts only if it ran the same way on those axes too.
+    // In all: the last sweep that agrees with s on the axes of (r + 1) | f.
+    __shared__ __align__(8) int8_t s_thr[16][8][8];    // (r = 7: padding): a node fetches its seven thresholds in one load
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int R = sweep_rounds(NT);
@@ -688,37 +712,19 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev + 3]
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
     for (int l = threadIdx.x; l < 8 * dstride; l += NT) s_dirty[l] = 0;
-    for (int e = threadIdx.x; e < 16 * 7 * 27; e += NT) {
-        const int cls = e % 27, r = (e / 27) % 7, s = e / (27 * 7), a = r + 1;
-        const int c3[3] = { cls % 3, (cls / 3) % 3, cls / 9 };
+    for (int e = threadIdx.x; e < 16 * 8 * 8; e += NT) {
+        const int r = e & 7, f = (e >> 3) & 7, s = e >> 6, mask = (r + 1) | f;
         int d[3], thr = -1;
         sweep_dir(s, d[0], d[1], d[2]);
         for (int sp = 0; sp < s; ++sp) {
             int e3[3];
             sweep_dir(sp, e3[0], e3[1], e3[2]);
             bool ok = true;
-            for (int ax = 0; ax < 3; ++ax) {
-                if (((a >> ax) & 1) && e3[ax] != d[ax]) ok = false;            // same neighbour upwind
-                if (e3[ax] > 0 ? c3[ax] == 0 : c3[ax] == 2) ok = false;        // the node was swept at all
-            }
+            for (int ax = 0; ax < 3; ++ax)
+                if (((mask >> ax) & 1) && e3[ax] != d[ax]) ok = false;
             if (ok) thr = sp + 1;
         }
-        s_thr[s][cls][r] = (int8_t)thr;
-    }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-        const int s = threadIdx.x;
-        int d[3], m = 127;
-        sweep_dir(s, d[0], d[1], d[2]);
-        for (int cls = 0; cls < 27; ++cls) {
-            const int c3[3] = { cls % 3, (cls / 3) % 3, cls / 9 };
-            bool present = true;
-            for (int ax = 0; ax < 3; ++ax)
-                if (d[ax] > 0 ? c3[ax] == 0 : c3[ax] == 2) present = false;
-            if (present)
-                for (int r = 0; r < 7; ++r) m = min(m, (int)s_thr[s][cls][r]);
-        }
-        s_tmin[s] = m;
+        s_thr[s][f][r] = (int8_t)thr;
     }
     __syncthreads();
     const int csize = CL ? (int)cluster_nctarank() : 1, crank = CL ? (int)cluster_ctarank() : 0;
@@ -731,10 +737,12 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     const float4* T = tri + 4 * tri_off[mesh];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
 
-    for (int s = 0; s < 16; ++s) {
+    // chg (optional): per-code change bitmaps of the mesh for tdf_sweep_bm_kernel, which takes over the later sweeps
+    uint32_t* const Cm = chg ? chg + (int64_t)mesh * 17 * act_words : nullptr;
+    for (int s = s_begin; s < s_end; ++s) {
         int di, dj, dk;
         sweep_dir(s, di, dj, dk);
-        const int tmin = s_tmin[s];
+        const int tmin = s_thr[s][7][6];            // the oldest threshold of the sweep: the last sweep in the same direction
         const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
         for (int L = 0; L < nlev; ++L) {
             // nothing upwind of this whole level has changed since it was last examined: every comparison the
@@ -759,9 +767,8 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     n = x0 + y0 + z0;
                     const int n0 = x1 + y0 + z0, n1 = x0 + y1 + z0, n2 = x1 + y1 + z0, n3 = x0 + y0 + z1,
                               n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
-                    const int cls = (i == 0 ? 0 : (i == ni - 1 ? 2 : 1)) + 3 * (j == 0 ? 0 : (j == nj - 1 ? 2 : 1)) +
-                                    9 * (k == 0 ? 0 : (k == nk - 1 ? 2 : 1));
-                    const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][cls][0]);   // bytes 0..3 | 4..6
+                    const int face = ((i == 0 || i == ni - 1) ? 1 : 0) | ((j == 0 || j == nj - 1) ? 2 : 0) | ((k == 0 || k == nk - 1) ? 4 : 0);
+                    const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][face][0]);   // bytes 0..3 | 4..6
                     const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
                                    w5 = Klo[2 * n5], w6 = Klo[2 * n6];
 #define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
@@ -827,6 +834,10 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                                            (ek > 0 ? pk - 1 : nk - 2 - pk);
                             s_dirty[dq * dstride + lv + 3] = code;
                         }
+                        if (Cm) {
+                            const int p = pi + ni * (pj + nj * pk);
+                            atomicOr(Cm + (s + 1) * act_words + (p >> 5), 1u << (p & 31));
+                        }
                     }
                 }
             };
@@ -853,6 +864,393 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
             }
             if (CL) cluster_barrier(); else __syncthreads();
         }
+    }
+    if (counter && n_eval) atomicAdd(counter + 1, n_eval);
+}
+
+// ------------------------------------------------- sweep, small grids ----
+// The sweep kernel for grids of at most 65,536 nodes (one CTA per mesh): the same three shortcuts as tdf_sweep_kernel
+// below, plus two that need one bit per grid node in shared memory.
+//   4. Activity bits. s_act (linear index i + ni (j + nj k)) marks the nodes that may have a candidate in this sweep: a
+//      SUPERSET of the nodes whose candidate test can pass (the exact test still runs for every node visited), built at
+//      the start of a sweep from per-code change bitmaps and extended by every change of the sweep itself. The nodes of
+//      a level are scanned against it and only the marked ones, compacted, run the node phase.
+//   5. Speculation. Once sweeps change few nodes, a sweep first visits ALL its marked nodes at once, level order ignored,
+//      against the state the sweep started from, and only notes which of them would change. A node whose upwind
+//      neighbours do not change during the sweep meets exactly that state when the reference visits it, so "would not
+//      change" is final for it. What is left -- the would-change nodes and, as changes happen, the nodes downwind of
+//      them -- is then swept level by level as usual; that is a handful of nodes, and levels without any are skipped.
+//      The second pass of a converged field costs one parallel visit per sweep instead of ~90 dependent level steps.
+
+// A node changed in sweep s: stamp its level in every direction, put the change on record under this sweep's code and
+// mark the 7 nodes downwind of it, which have a new candidate in this very sweep (they lie on later levels; lvcnt counts
+// the marked nodes per level).
+template <bool SP>
+__device__ __forceinline__ void sweep_record_change(uint32_t pos, int s, int di, int dj, int dk, int ni, int nj, int nk,
+                                                    int dstride, uint8_t* s_dirty, uint32_t* chg_code, uint32_t* s_act,
+                                                    uint32_t* s_lvcnt)
+{
+    const uint8_t code = (uint8_t)(s + 1);
+    const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
+    int lv_s = 0;
+#pragma unroll
+    for (int dq = 0; dq < 8; ++dq) {            // (codes only grow and all writers of a sweep write the same value)
+        int ei, ej, ek;
+        sweep_dir(dq, ei, ej, ek);
+        const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) + (ek > 0 ? pk - 1 : nk - 2 - pk);
+        s_dirty[dq * dstride + lv + 3] = code;
+        if (dq == (s & 7)) lv_s = lv;
+    }
+    const int p = pi + ni * (pj + nj * pk);
+    atomicOr(chg_code + (p >> 5), 1u << (p & 31));
+    if (!SP) return;                            // (no activity bits in a plain sweep)
+    const bool ox = (unsigned)(pi + di) < (unsigned)ni, oy = (unsigned)(pj + dj) < (unsigned)nj,
+               oz = (unsigned)(pk + dk) < (unsigned)nk;
+    const int sx = di, sy = dj * ni, sz = dk * ni * nj;
+#pragma unroll
+    for (int a = 1; a < 8; ++a) {
+        const bool in = (!(a & 1) || ox) && (!(a & 2) || oy) && (!(a & 4) || oz);
+        if (in) {
+            const int pp = p + ((a & 1) ? sx : 0) + ((a & 2) ? sy : 0) + ((a & 4) ? sz : 0);
+            const uint32_t bit = 1u << (pp & 31);
+            const uint32_t old = atomicOr(&s_act[pp >> 5], bit);
+            if (!(old & bit)) atomicAdd(&s_lvcnt[lv_s + ((a & 1) + ((a >> 1) & 1) + (a >> 2))], 1u);
+        }
+    }
+}
+
+// code-0 change bitmap of a mesh: the nodes that hold a triangle after the band init (all threads of the CTA)
+__device__ __noinline__ void sweep_init_bitmap(const uint32_t* Klo, KeyMap km, int ni, int nj, int nk, uint32_t* Cm, int act_words)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nvox = ni * nj * nk;
+    for (int w = warp; w < act_words; w += (int)(blockDim.x >> 5)) {
+        const int p = 32 * w + lane;
+        bool has = false;
+        if (p < nvox) {
+            const int i = p % ni, r = p / ni, j = r % nj, k = r / nj;
+            has = (Klo[2 * (kx(i) + ky(j, km.sbj) + kz(k, km.sbk))] & kTriMask) != kTriMask;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) Cm[w] = m;
+    }
+    __syncthreads();
+}
+
+// s_act for sweep s (all threads of the CTA). Node n has a candidate at slot r iff its neighbour m = n - d*r holds a
+// triangle and changed in a sweep after the one in which n last examined it, i.e. iff m is in the union of the change
+// bitmaps of the codes above the slot's threshold; that union, shifted by the slot's offset in the linear index, marks the
+// nodes n. Interior nodes use their exact thresholds (thw: the seven bytes of s_thr[s][0]); nodes on a grid face, whose
+// thresholds are older, use the oldest one of the sweep (tmin). Shifts that run across a row end only set extra bits.
+__device__ __noinline__ void sweep_build_activity(int s, int tmin, uint2 thw, const uint32_t* Cm, int act_words,
+                                                  const uint32_t* __restrict__ bnd, uint32_t* s_act, int ni, int nj)
+{
+    int di, dj, dk;
+    sweep_dir(s, di, dj, dk);
+    for (int w = threadIdx.x; w < act_words; w += (int)blockDim.x) s_act[w] = 0u;
+    __syncthreads();
+    int th[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) th[r] = (int)(int8_t)((r < 4 ? thw.x : thw.y) >> (8 * (r & 3)));
+    const int nc = s - tmin;                           // codes tmin + 1 .. s: at most 8 (first pass: s + 1; second: 7)
+    for (int w = threadIdx.x; w < act_words; w += (int)blockDim.x) {
+        uint32_t cw[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cw[q] = q < nc ? __ldcg(Cm + (s - q) * act_words + w) : 0u;
+        uint32_t acc = 0u, v[7] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            acc |= cw[q];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) if (th[r] + 1 == s - q) v[r] = acc;
+        }
+        if (acc == 0u) continue;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const int a = r + 1;
+            const int delta = ((a & 1) ? di : 0) + ((a & 2) ? dj * ni : 0) + ((a & 4) ? dk * ni * nj : 0);
+            const int bit = 32 * w + delta;
+            const int wd = bit >> 5, sh = bit & 31;             // arithmetic shift: floor for negative bit positions
+            const uint32_t lo_i = v[r] << sh, lo_b = acc << sh;
+            const uint32_t hi_i = sh ? v[r] >> (32 - sh) : 0u, hi_b = sh ? acc >> (32 - sh) : 0u;
+            if (wd >= 0 && wd < act_words && lo_b) {
+                const uint32_t val = lo_i | (lo_b & __ldg(bnd + wd));
+                if (val) atomicOr(&s_act[wd], val);
+            }
+            if (wd + 1 >= 0 && wd + 1 < act_words && hi_b) {
+                const uint32_t val = hi_i | (hi_b & __ldg(bnd + wd + 1));
+                if (val) atomicOr(&s_act[wd + 1], val);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 7 : (NT == 256 ? 3 : 1))
+tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
+                    const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
+                    int lev_words, g3d_tdf_params P, u64* counter, uint32_t* chg, const uint32_t* __restrict__ bnd,
+                    int act_words, int s_begin, int s_end, int spec_div)
+{
+    u64 n_eval = 0;
+    extern __shared__ uint32_t s_mem[];
+    __shared__ __align__(8) int8_t s_thr[16][8][8];    // as in tdf_sweep_kernel
+    __shared__ int s_nchg;                             // nodes changed in the sweep so far
+    int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    constexpr int R = sweep_rounds(NT);
+    uint32_t* q_tri = s_mem + lev_words + warp * (2 * R * kSweepQueue);
+    uint32_t* q_pos = q_tri + R * kSweepQueue;
+    const int dstride = nlev + 3;
+    uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev + 3]
+    uint32_t* s_act = s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue) + (8 * dstride + 3) / 4;        // [act_words]
+    uint32_t* s_lvcnt = s_act + act_words;             // [nlev + 4]: marked nodes per level (speculative sweeps)
+    uint32_t* s_list = q_tri;                          // the nodes waiting for a batch; the queue is idle while they collect
+    for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
+    // (taking over from tdf_sweep_kernel after sweep s_begin - 1: its level stamps are gone, so a plain sweep here skips no level)
+    for (int l = threadIdx.x; l < 8 * dstride; l += NT) s_dirty[l] = s_begin ? 255 : 0;
+    for (int e = threadIdx.x; e < 16 * 8 * 8; e += NT) {
+        const int r = e & 7, f = (e >> 3) & 7, s = e >> 6, mask = (r + 1) | f;
+        int d[3], thr = -1;
+        sweep_dir(s, d[0], d[1], d[2]);
+        for (int sp = 0; sp < s; ++sp) {
+            int e3[3];
+            sweep_dir(sp, e3[0], e3[1], e3[2]);
+            bool ok = true;
+            for (int ax = 0; ax < 3; ++ax)
+                if (((mask >> ax) & 1) && e3[ax] != d[ax]) ok = false;
+            if (ok) thr = sp + 1;
+        }
+        s_thr[s][f][r] = (int8_t)thr;
+    }
+    if (threadIdx.x == 0) s_nchg = s_begin ? 0 : 0x7fffffff;
+    const int mesh = blockIdx.x;
+    const KeyMap km = keymap_of(P);
+    u64* K = key + (int64_t)mesh * km.stride;
+    const uint32_t* Klo = (const uint32_t*)K;
+    const float4* T = tri + 4 * tri_off[mesh];
+    const int ni = P.ni, nj = P.nj, nk = P.nk;
+    const int n_lattice = (ni - 1) * (nj - 1) * (nk - 1);
+    // change bitmaps of this mesh, one per code (0 = the band init, s + 1 = sweep s), zero at launch
+    uint32_t* Cm = chg + (int64_t)mesh * 17 * act_words;
+    __syncthreads();
+    if (s_begin == 0) {
+        sweep_init_bitmap(Klo, km, ni, nj, nk, Cm, act_words);
+    } else {                                        // the nodes sweep s_begin - 1 changed
+        int c = 0;
+        for (int w = threadIdx.x; w < act_words; w += NT) c += __popc(__ldcg(Cm + s_begin * act_words + w));
+        if (c) atomicAdd(&s_nchg, c);
+    }
+
+    // One sweep. SP = false: the plain level-synchronous sweep of tdf_sweep_kernel (every node of every level that is not
+    // skipped whole), for sweeps that still change many nodes. SP = true: activity bits + speculation.
+    auto sweep = [&](auto sp_tag, const int s) {
+        constexpr bool SP = decltype(sp_tag)::value;
+        int di, dj, dk;
+        sweep_dir(s, di, dj, dk);
+        const int tmin = s_thr[s][7][6];            // the oldest threshold of the sweep: the last sweep in the same direction
+        const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
+        if (SP) {
+            for (int l = threadIdx.x; l < nlev + 4; l += NT) s_lvcnt[l] = 0u;
+            if (s <= 7) {
+                // first pass: each sweep brings neighbours no sweep has looked at before, so about every node that has a
+                // neighbour with a triangle is active: all bits on, no bitmap arithmetic
+                for (int w = threadIdx.x; w < act_words; w += NT) s_act[w] = 0xffffffffu;
+                __syncthreads();
+            } else {
+                sweep_build_activity(s, tmin, *reinterpret_cast<const uint2*>(&s_thr[s][0][0]), Cm, act_words, bnd, s_act, ni, nj);
+            }
+        }
+        uint32_t* const chg_code = Cm + (s + 1) * act_words;
+        int n_changed = 0;                          // this thread's nodes changed in the sweep
+        for (int pass = SP ? 0 : 1; pass < 2; ++pass) {
+        const bool flat = SP && pass == 0;          // the speculative visit of every marked node, levels ignored
+        for (int L = 0; L < (flat ? 1 : nlev); ++L) {
+            int beg, end;
+            if (flat) {
+                beg = 0; end = s_lev[nlev];
+            } else {
+                if (SP) { if (((const volatile uint32_t*)s_lvcnt)[L] == 0u) continue; }   // no marked node on this level
+                // nothing upwind of this whole level has changed since it was last examined
+                else if (max(max((int)dirty[L], (int)dirty[L + 1]), (int)dirty[L + 2]) <= tmin) continue;
+                beg = s_lev[L]; end = s_lev[L + 1];
+            }
+            // node phase of one round: candidates of this lane's node go to the queue from slot `qbase` on; returns
+            // the number of pairs the warp queued (warp-uniform)
+            auto node_phase = [&](bool valid, uint32_t pos, int qbase, uint32_t& need, float& phi, int& ct, int& n, int& off) -> int {
+                int c0 = -1, c1 = -1, c2 = -1, c3 = -1, c4 = -1, c5 = -1, c6 = -1;
+                need = 0; phi = 0.f; ct = -1; n = 0; off = 0;
+                if (valid) {
+                    const int i = (int)(pos & 1023u), j = (int)((pos >> 10) & 1023u), k = (int)(pos >> 20);
+                    const int x0 = kx(i), x1 = kx(i - di), y0 = ky(j, km.sbj), y1 = ky(j - dj, km.sbj),
+                              z0 = kz(k, km.sbk), z1 = kz(k - dk, km.sbk);
+                    n = x0 + y0 + z0;
+                    const int n0 = x1 + y0 + z0, n1 = x0 + y1 + z0, n2 = x1 + y1 + z0, n3 = x0 + y0 + z1,
+                              n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
+                    const int face = ((i == 0 || i == ni - 1) ? 1 : 0) | ((j == 0 || j == nj - 1) ? 2 : 0) | ((k == 0 || k == nk - 1) ? 4 : 0);
+                    const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][face][0]);   // bytes 0..3 | 4..6
+                    const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
+                                   w5 = Klo[2 * n5], w6 = Klo[2 * n6];
+#define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
+#define G3D_CAND(w, thr) (((int)((w) >> 27) > (thr) && ((w) & kTriMask) != kTriMask) ? (int)((w) & kTriMask) : -1)
+                    c0 = G3D_CAND(w0, G3D_THR(thw.x, 0)); c1 = G3D_CAND(w1, G3D_THR(thw.x, 1)); c2 = G3D_CAND(w2, G3D_THR(thw.x, 2));
+                    c3 = G3D_CAND(w3, G3D_THR(thw.x, 3)); c4 = G3D_CAND(w4, G3D_THR(thw.y, 0)); c5 = G3D_CAND(w5, G3D_THR(thw.y, 1));
+                    c6 = G3D_CAND(w6, G3D_THR(thw.y, 2));
+#undef G3D_CAND
+#undef G3D_THR
+                    if ((c0 & c1 & c2 & c3 & c4 & c5 & c6) >= 0) {      // some neighbour holds a triangle worth trying
+                        u64 kv = K[n];
+                        phi = __uint_as_float((uint32_t)(kv >> 32));
+                        ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);
+                        need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
+                        need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
+                        need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
+                        need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
+                        need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
+                        need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
+                        need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, need != 0)) return 0;
+                const int cnt = __popc(need);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                off = qbase + incl - cnt;
+                int w = off;
+                if (need & 1u)  { q_tri[w] = c0; q_pos[w] = pos; ++w; }
+                if (need & 2u)  { q_tri[w] = c1; q_pos[w] = pos; ++w; }
+                if (need & 4u)  { q_tri[w] = c2; q_pos[w] = pos; ++w; }
+                if (need & 8u)  { q_tri[w] = c3; q_pos[w] = pos; ++w; }
+                if (need & 16u) { q_tri[w] = c4; q_pos[w] = pos; ++w; }
+                if (need & 32u) { q_tri[w] = c5; q_pos[w] = pos; ++w; }
+                if (need & 64u) { q_tri[w] = c6; q_pos[w] = pos; ++w; }
+                return __shfl_sync(0xffffffffu, incl, 31);
+            };
+            // the owner replays the results of its pairs in neighbour order (they lie in that order from `off` on).
+            // Speculative visit: nothing is stored; a node that would not change loses its mark, one that would keeps it
+            // and is counted on its level.
+            auto apply = [&](bool valid, uint32_t need, uint32_t pos, float phi, int ct, int n, int off) {
+                bool changed = false;
+                for (int w = off; need; need &= need - 1, ++w) {
+                    const float d = __uint_as_float(q_pos[w]);
+                    if (d < phi) { phi = d; ct = (int)q_tri[w]; changed = true; }
+                }
+                if (flat) {
+                    if (valid) {
+                        const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
+                        if (changed) {
+                            const int lv = (di > 0 ? pi - 1 : ni - 2 - pi) + (dj > 0 ? pj - 1 : nj - 2 - pj) + (dk > 0 ? pk - 1 : nk - 2 - pk);
+                            atomicAdd(&s_lvcnt[lv], 1u);
+                        } else {
+                            const int p = pi + ni * (pj + nj * pk);
+                            atomicAnd(&s_act[p >> 5], ~(1u << (p & 31)));
+                        }
+                    }
+                } else if (changed) {
+                    K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)(s + 1) << 27) | (uint32_t)ct;
+                    ++n_changed;
+                    sweep_record_change<SP>(pos, s, di, dj, dk, ni, nj, nk, dstride, s_dirty, chg_code, s_act, s_lvcnt);
+                }
+            };
+            int ln = 0;                                 // SP: nodes waiting in s_list (warp-uniform)
+            for (int qb = beg + warp * 32; ; qb += R * NT) {
+                bool vA = false, vB = false, kp0 = false, kp1 = false;
+                uint32_t posA = 0, posB = 0, keep0 = 0, keep1 = 0;
+                auto node_at = [&](int q, uint32_t& pos) -> bool {
+                    if (q >= end) return false;
+                    const uint32_t o = __ldg(order + q);
+                    const int a = o & 1023, b = (o >> 10) & 1023, c = o >> 20;
+                    const int i = di > 0 ? 1 + a : ni - 2 - a;
+                    const int j = dj > 0 ? 1 + b : nj - 2 - b;
+                    const int k = dk > 0 ? 1 + c : nk - 2 - c;
+                    pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+                    if (!SP) return true;
+                    const int p = i + ni * (j + nj * k);
+                    return (s_act[p >> 5] >> (p & 31)) & 1u;
+                };
+                if (SP) {
+                    // scan R rounds against the activity bits. Where most nodes are active they go straight on; otherwise
+                    // the active ones collect in s_list and a batch runs when 32 R are waiting, or with what is left once
+                    // the range has been scanned
+                    const bool more = qb < end;
+                    bool direct = false;
+                    if (more) {
+                        vA = node_at(qb + lane, posA);
+                        if (R == 2) vB = node_at(qb + NT + lane, posB);
+                        const uint32_t m0 = __ballot_sync(0xffffffffu, vA), m1 = R == 2 ? __ballot_sync(0xffffffffu, vB) : 0u;
+                        const int c0 = __popc(m0), c1 = __popc(m1);
+                        if (c0 + c1 == 0) continue;
+                        direct = ln == 0 && c0 + c1 >= 20 * R;
+                        if (!direct) {
+                            if (vA) s_list[ln + __popc(m0 & lt)] = posA;
+                            if (R == 2 && vB) s_list[ln + c0 + __popc(m1 & lt)] = posB;
+                            ln += c0 + c1;
+                            if (ln < 32 * R) continue;
+                        }
+                    } else if (ln == 0) {
+                        break;
+                    }
+                    if (!direct) {
+                        __syncwarp();
+                        const int cn = min(ln, 32 * R);
+                        vA = lane < cn;
+                        if (vA) posA = s_list[lane];
+                        if (R == 2) { vB = 32 + lane < cn; if (vB) posB = s_list[32 + lane]; }
+                        // fewer than 32 R nodes stay behind, in registers while the queue is in use
+                        kp0 = cn + lane < ln;
+                        if (kp0) keep0 = s_list[cn + lane];
+                        if (R == 2) { kp1 = cn + 32 + lane < ln; if (kp1) keep1 = s_list[cn + 32 + lane]; }
+                        __syncwarp();
+                        ln -= cn;
+                    }
+                } else {
+                    if (qb >= end) break;
+                    vA = node_at(qb + lane, posA);
+                    if (R == 2) vB = node_at(qb + NT + lane, posB);
+                }
+                uint32_t needA, needB = 0;
+                float phiA, phiB = 0.f;
+                int ctA, nA, offA, ctB = -1, nB = 0, offB = 0;
+                int W = node_phase(vA, posA, 0, needA, phiA, ctA, nA, offA);
+                if (R == 2 && (SP ? __any_sync(0xffffffffu, vB) : qb + NT < end)) W += node_phase(vB, posB, W, needB, phiB, ctB, nB, offB);
+                if (W != 0) {
+                    __syncwarp();
+                    for (int e = lane; e < W; e += 32) {
+                        uint32_t pp = q_pos[e];
+                        V3 gx = node_pos((int)(pp & 1023u), (int)((pp >> 10) & 1023u), (int)(pp >> 20), P);
+                        q_pos[e] = __float_as_uint(point_triangle_distance(gx, load_trirec(T + 4 * (int64_t)q_tri[e])));
+                        ++n_eval;
+                    }
+                    __syncwarp();
+                }
+                if (W != 0 || flat) {
+                    apply(vA, needA, posA, phiA, ctA, nA, offA);
+                    if (R == 2) apply(vB, needB, posB, phiB, ctB, nB, offB);
+                    __syncwarp();                   // the queue is free again
+                }
+                if (SP && kp0) s_list[lane] = keep0;
+                if (SP && R == 2 && kp1) s_list[32 + lane] = keep1;
+            }
+            __syncthreads();
+        }
+        }
+        if (n_changed) atomicAdd(&s_nchg, n_changed);
+    };
+
+    for (int s = s_begin; s < s_end; ++s) {
+        // activity bits + speculation once the previous sweep changed few nodes (spec_div: tuning / test knob, 0 = never)
+        __syncthreads();
+        const int prev = s_nchg;
+        // (spec_div < 0: always, from sweep 1 on -- tests)
+        const bool spec = spec_div < 0 ? s >= 1 : (spec_div > 0 && s >= 8 && (int64_t)prev * spec_div <= (int64_t)n_lattice);
+        __syncthreads();
+        if (threadIdx.x == 0) s_nchg = 0;
+        if (spec) sweep(std::true_type(), s); else sweep(std::false_type(), s);
     }
     if (counter && n_eval) atomicAdd(counter + 1, n_eval);
 }
@@ -955,10 +1353,18 @@ int grid_for(int64_t n, int block, int max_blocks)
 }  // namespace
 
 namespace {
+// timing aid only: fewer than the reference's 16 sweeps
+inline int sweep_count_env()
+{
+    const char* e_ns = getenv("G3D_SWEEP_COUNT");
+    return e_ns ? atoi(e_ns) : 16;
+}
+
 template <int NT, bool CL>
 int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p,
-                    u64* cnt, cudaStream_t stream)
+                    u64* cnt, cudaStream_t stream, int s_begin = 0, int s_end = 16, uint32_t* chg = nullptr)
 {
+    s_end = min(s_end, sweep_count_env());
     const int lev_words = (nlev + 1 + 3) & ~3;
     const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue) * 4 + (size_t)8 * (nlev + 3);
     auto kern = tdf_sweep_kernel<NT, CL>;
@@ -976,8 +1382,38 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
     cfg.attrs = attr;
     cfg.numAttrs = CL ? 1 : 0;
     G3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, w.key, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
-                                    (const int32_t*)w.level_start, nlev, lev_words, p, cnt));
+                                    (const int32_t*)w.level_start, nlev, lev_words, p, cnt, s_begin, s_end, chg, w.act_words));
     return G3D_OK;
+}
+
+// the small-grid kernel (activity bits + speculation), one CTA per mesh
+template <int NT>
+int launch_sweep_bm(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
+                    cudaStream_t stream, int s_begin)
+{
+    const int lev_words = (nlev + 1 + 3) & ~3;
+    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue + (8 * (nlev + 3) + 3) / 4 +
+                                 w.act_words + nlev + 4) * 4;
+    auto kern = tdf_sweep_bm_kernel<NT>;
+    G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // speculate once a sweep changed at most 1/8 of the lattice nodes; G3D_SWEEP_SPEC overrides the divisor (0 = never)
+    const char* e_sp = getenv("G3D_SWEEP_SPEC");
+    const int spec_div = e_sp ? atoi(e_sp) : 8;
+    kern<<<(unsigned)n_mesh, NT, smem, stream>>>(w.key, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
+                                                 (const int32_t*)w.level_start, nlev, lev_words, p, cnt, w.chg,
+                                                 (const uint32_t*)w.bnd, w.act_words, s_begin, min(16, sweep_count_env()), spec_div);
+    return G3D_OK;
+}
+
+template <int NT>
+int sweep_two_kernels(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
+                      cudaStream_t stream, int split)
+{
+    if (split > 0) {
+        int rc = launch_sweep_nt<NT, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream, 0, split, w.chg);
+        if (rc != G3D_OK) return rc;
+    }
+    return split < 16 ? launch_sweep_bm<NT>(n_mesh, nlev, w, tri_off, p, cnt, stream, split) : G3D_OK;
 }
 
 int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
@@ -1007,12 +1443,24 @@ int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, c
     if (forced) nt = forced;
     if (forced_cl) { csize = forced_cl; nt = 1024; }
     if (csize > 1) return launch_sweep_nt<1024, true>(n_mesh, csize, nlev, w, tri_off, p, cnt, stream);
+    // grids of at most 65,536 nodes: the kernel with one activity bit per node in shared memory; G3D_SWEEP_BITMAP=0 turns
+    // it off (tests run both)
+    const char* e_bm = getenv("G3D_SWEEP_BITMAP");
+    const bool bm = w.act_words > 0 && !(e_bm && atoi(e_bm) == 0);
+    // first pass: the plain kernel, which also puts every change on record; second pass: the bitmap kernel. (G3D_SWEEP_SPLIT:
+    // the sweep at which it takes over, 0 = from the start -- tests and tuning.)
+    const char* e_split = getenv("G3D_SWEEP_SPLIT");
+    const int split = e_split ? max(0, min(16, atoi(e_split))) : 8;
+    if (bm) G3D_CUDA_TRY(cudaMemsetAsync(w.chg, 0, (size_t)n_mesh * 17 * w.act_words * 4, stream));
+#define G3D_SWEEP_CASE(N) (!bm ? launch_sweep_nt<N, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream) \
+                               : sweep_two_kernels<N>(n_mesh, nlev, w, tri_off, p, cnt, stream, split))
     switch (nt) {
-        case 128: return launch_sweep_nt<128, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
-        case 512: return launch_sweep_nt<512, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
-        case 1024: return launch_sweep_nt<1024, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
-        default: return launch_sweep_nt<256, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream);
+        case 128: return G3D_SWEEP_CASE(128);
+        case 512: return G3D_SWEEP_CASE(512);
+        case 1024: return G3D_SWEEP_CASE(1024);
+        default: return G3D_SWEEP_CASE(256);
     }
+#undef G3D_SWEEP_CASE
 }
 }  // namespace
 
@@ -1186,7 +1634,7 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
         const int nlev = nlev_of(p);
         if (total_tris > 0 && nlev > 0) {
             size_t smem = (size_t)(nlev + 1 + (p.ni - 1) + (p.nj - 1) - 1) * 4;
-            tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start);
+            tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start, w.bnd, w.act_words);
             prof_mark(ST_ORDER, stream);
             int rc = launch_sweep(n_mesh, nlev, w, tri_off, p, cnt, stream);
             if (rc != G3D_OK) return rc;

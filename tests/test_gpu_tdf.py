@@ -374,16 +374,29 @@ def test_host_abi_chunked_path_equals_device_abi(g3d, count, n):
     L.g3d_context_destroy(ctx)
 
 
-@pytest.mark.parametrize("tiled,sweep_threads", [(None, None), ("1", None), ("1", "128"), ("0", "256")])
-def test_randomised_parity_campaign(g3d, tiled, sweep_threads):
+@pytest.mark.parametrize("tiled,sweep_threads,bitmap", [(None, None, None), ("1", None, None), ("1", "128", None),
+                                                        ("0", "256", None), ("1", "128", "0"), (None, None, "0"),
+                                                        ("1", "128", "spec"), (None, None, "spec"), ("1", "256", "split3")])
+def test_randomised_parity_campaign(g3d, tiled, sweep_threads, bitmap):
     """A short run of tools/fuzz_parity.py (random soups, degenerate / huge triangles, random grids and poses), once
     with the kernel choice left to the library (single meshes: scatter band init, 1,024-thread sweeps) and then with
     the batch-sized kernels forced onto every case: tiled band init, 128- and 256-thread sweep CTAs (two rounds of a
-    level per evaluation queue)."""
+    level per evaluation queue); with the small-grid sweep kernel (activity bits + speculation) switched off (the
+    plain kernel that larger grids take), made to run all 16 sweeps and to speculate in every one of them ("spec"), and
+    taking over after sweep 2 ("split3")."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
     env.pop("G3D_INIT_TILED", None)
     env.pop("G3D_SWEEP_THREADS", None)
+    env.pop("G3D_SWEEP_BITMAP", None)
+    for k in ("G3D_SWEEP_SPEC", "G3D_SWEEP_SPLIT"):
+        env.pop(k, None)
+    if bitmap == "0":
+        env["G3D_SWEEP_BITMAP"] = "0"
+    elif bitmap == "spec":
+        env["G3D_SWEEP_SPEC"], env["G3D_SWEEP_SPLIT"] = "-1", "0"
+    elif bitmap == "split3":
+        env["G3D_SWEEP_SPEC"], env["G3D_SWEEP_SPLIT"] = "-1", "3"
     if tiled:
         env["G3D_INIT_TILED"] = tiled
     if sweep_threads:
