@@ -683,6 +683,48 @@ __device__ __forceinline__ void cluster_barrier()
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 
+// ---- candidate selection of a sweep visit (shared by both sweep kernels) ----
+__device__ __forceinline__ int tri_of(uint32_t w) { return (w & kTriMask) != kTriMask ? (int)(w & kTriMask) : -1; }
+// bit r: the change code of neighbour r is not above the node's threshold for slot r (thw: the seven threshold bytes)
+__device__ __forceinline__ uint32_t examined_mask(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                                  uint32_t w6, uint2 thw)
+{
+#define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
+    uint32_t xm = 0;
+    xm |= (int)(w0 >> 27) <= G3D_THR(thw.x, 0) ? 1u : 0u;
+    xm |= (int)(w1 >> 27) <= G3D_THR(thw.x, 1) ? 2u : 0u;
+    xm |= (int)(w2 >> 27) <= G3D_THR(thw.x, 2) ? 4u : 0u;
+    xm |= (int)(w3 >> 27) <= G3D_THR(thw.x, 3) ? 8u : 0u;
+    xm |= (int)(w4 >> 27) <= G3D_THR(thw.y, 0) ? 16u : 0u;
+    xm |= (int)(w5 >> 27) <= G3D_THR(thw.y, 1) ? 32u : 0u;
+    xm |= (int)(w6 >> 27) <= G3D_THR(thw.y, 2) ? 64u : 0u;
+#undef G3D_THR
+    return xm;
+}
+// Which candidates need an evaluation. A candidate cannot pass the strict `<` when it is the node's own triangle, an
+// earlier candidate of the same visit, or the triangle of ANY upwind neighbour that has not changed since the node last
+// examined it: the node met that triangle then (evaluated it, or skipped it for one of these very reasons), and phi has
+// only decreased since. The last case costs nothing to detect -- the seven words are loaded anyway -- and removes four
+// evaluations in ten (the same triangle reaching a node through a second neighbour).
+__device__ __forceinline__ uint32_t sweep_need_mask(const int (&a)[7], uint32_t xm, uint32_t cm, int ct)
+{
+    // one comparison per pair of slots: eq[q] bit r = slots q < r hold the same triangle. Then slot r is dropped (an earlier
+    // slot holds its triangle: a candidate evaluated first, or a neighbour examined before), and slot q is dropped when one
+    // of its later twins is an examined neighbour. (Two empty slots compare equal too; they are no candidates anyway.)
+    uint32_t drop = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) drop |= a[r] == ct ? 1u << r : 0u;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        uint32_t eq = 0;
+#pragma unroll
+        for (int r = q + 1; r < 7; ++r) eq |= a[q] == a[r] ? 1u << r : 0u;
+        drop |= eq;
+        drop |= (eq & xm) ? 1u << q : 0u;
+    }
+    return cm & ~drop;
+}
+
 template <int NT, bool CL>
 __global__ void __launch_bounds__(NT)
 tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
@@ -771,24 +813,19 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][face][0]);   // bytes 0..3 | 4..6
                     const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
                                    w5 = Klo[2 * n5], w6 = Klo[2 * n6];
-#define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
-#define G3D_CAND(w, thr) (((int)((w) >> 27) > (thr) && ((w) & kTriMask) != kTriMask) ? (int)((w) & kTriMask) : -1)
-                    c0 = G3D_CAND(w0, G3D_THR(thw.x, 0)); c1 = G3D_CAND(w1, G3D_THR(thw.x, 1)); c2 = G3D_CAND(w2, G3D_THR(thw.x, 2));
-                    c3 = G3D_CAND(w3, G3D_THR(thw.x, 3)); c4 = G3D_CAND(w4, G3D_THR(thw.y, 0)); c5 = G3D_CAND(w5, G3D_THR(thw.y, 1));
-                    c6 = G3D_CAND(w6, G3D_THR(thw.y, 2));
-#undef G3D_CAND
-#undef G3D_THR
-                    if ((c0 & c1 & c2 & c3 & c4 & c5 & c6) >= 0) {      // some neighbour holds a triangle worth trying
+                    // ta[r]: the neighbour's triangle (-1: none); xm bit r: the neighbour has not changed since this node last
+                    // examined it; cm bit r: it is a candidate
+                    const int ta[7] = { tri_of(w0), tri_of(w1), tri_of(w2), tri_of(w3), tri_of(w4), tri_of(w5), tri_of(w6) };
+                    const uint32_t xm = examined_mask(w0, w1, w2, w3, w4, w5, w6, thw);
+                    uint32_t cm = 0;
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) cm |= (ta[r] >= 0 && !((xm >> r) & 1u)) ? 1u << r : 0u;
+                    c0 = ta[0]; c1 = ta[1]; c2 = ta[2]; c3 = ta[3]; c4 = ta[4]; c5 = ta[5]; c6 = ta[6];
+                    if (cm) {                                            // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
                         phi = __uint_as_float((uint32_t)(kv >> 32));
                         ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);
-                        need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
-                        need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
-                        need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
-                        need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
-                        need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
-                        need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
-                        need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                        need = sweep_need_mask(ta, xm, cm, ct);
                     }
                 }
                 if (!__any_sync(0xffffffffu, need != 0)) return 0;
@@ -1092,24 +1129,19 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                     const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][face][0]);   // bytes 0..3 | 4..6
                     const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
                                    w5 = Klo[2 * n5], w6 = Klo[2 * n6];
-#define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
-#define G3D_CAND(w, thr) (((int)((w) >> 27) > (thr) && ((w) & kTriMask) != kTriMask) ? (int)((w) & kTriMask) : -1)
-                    c0 = G3D_CAND(w0, G3D_THR(thw.x, 0)); c1 = G3D_CAND(w1, G3D_THR(thw.x, 1)); c2 = G3D_CAND(w2, G3D_THR(thw.x, 2));
-                    c3 = G3D_CAND(w3, G3D_THR(thw.x, 3)); c4 = G3D_CAND(w4, G3D_THR(thw.y, 0)); c5 = G3D_CAND(w5, G3D_THR(thw.y, 1));
-                    c6 = G3D_CAND(w6, G3D_THR(thw.y, 2));
-#undef G3D_CAND
-#undef G3D_THR
-                    if ((c0 & c1 & c2 & c3 & c4 & c5 & c6) >= 0) {      // some neighbour holds a triangle worth trying
+                    // ta[r]: the neighbour's triangle (-1: none); xm bit r: the neighbour has not changed since this node last
+                    // examined it; cm bit r: it is a candidate
+                    const int ta[7] = { tri_of(w0), tri_of(w1), tri_of(w2), tri_of(w3), tri_of(w4), tri_of(w5), tri_of(w6) };
+                    const uint32_t xm = examined_mask(w0, w1, w2, w3, w4, w5, w6, thw);
+                    uint32_t cm = 0;
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) cm |= (ta[r] >= 0 && !((xm >> r) & 1u)) ? 1u << r : 0u;
+                    c0 = ta[0]; c1 = ta[1]; c2 = ta[2]; c3 = ta[3]; c4 = ta[4]; c5 = ta[5]; c6 = ta[6];
+                    if (cm) {                                            // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
                         phi = __uint_as_float((uint32_t)(kv >> 32));
                         ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);
-                        need |= (c0 >= 0 && c0 != ct) ? 1u : 0u;
-                        need |= (c1 >= 0 && c1 != ct && c1 != c0) ? 2u : 0u;
-                        need |= (c2 >= 0 && c2 != ct && c2 != c0 && c2 != c1) ? 4u : 0u;
-                        need |= (c3 >= 0 && c3 != ct && c3 != c0 && c3 != c1 && c3 != c2) ? 8u : 0u;
-                        need |= (c4 >= 0 && c4 != ct && c4 != c0 && c4 != c1 && c4 != c2 && c4 != c3) ? 16u : 0u;
-                        need |= (c5 >= 0 && c5 != ct && c5 != c0 && c5 != c1 && c5 != c2 && c5 != c3 && c5 != c4) ? 32u : 0u;
-                        need |= (c6 >= 0 && c6 != ct && c6 != c0 && c6 != c1 && c6 != c2 && c6 != c3 && c6 != c4 && c6 != c5) ? 64u : 0u;
+                        need = sweep_need_mask(ta, xm, cm, ct);
                     }
                 }
                 if (!__any_sync(0xffffffffu, need != 0)) return 0;

@@ -44,6 +44,22 @@ void sweep_stats(const uint32_t *tri, int64_t ntri, const float *x, const float 
                     ++o[0];
                     int cand[7], ncand = 0, active = 0, evals = 0, changed = 0;
                     float gx[3] = { p[0] * dx + origin[0], p[1] * dx + origin[1], p[2] * dx + origin[2] };
+                    int ex_t[7], n_ex = 0;              /* triangles of upwind neighbours already examined and unchanged since */
+                    for (int r = 1; r <= 7; ++r) {
+                        int m[3] = { p[0] - ((r & 1) ? d[0] : 0), p[1] - ((r & 2) ? d[1] : 0), p[2] - ((r & 4) ? d[2] : 0) };
+                        size_t qm = (size_t)m[0] + (size_t)ni * (m[1] + (size_t)nj * m[2]);
+                        int thr = -1;
+                        for (int sp = 0; sp < s; ++sp) {
+                            int e[3], ok = 1;
+                            sdir(sp, e);
+                            for (int ax = 0; ax < 3; ++ax) {
+                                if (((r >> ax) & 1) && e[ax] != d[ax]) ok = 0;
+                                if (e[ax] > 0 ? p[ax] == 0 : p[ax] == dims[ax] - 1) ok = 0;
+                            }
+                            if (ok) thr = sp + 1;
+                        }
+                        if (ct[qm] >= 0 && stamp[qm] <= thr) ex_t[n_ex++] = ct[qm];
+                    }
                     for (int r = 1; r <= 7; ++r) {
                         int m[3] = { p[0] - ((r & 1) ? d[0] : 0), p[1] - ((r & 2) ? d[1] : 0), p[2] - ((r & 4) ? d[2] : 0) };
                         size_t qm = (size_t)m[0] + (size_t)ni * (m[1] + (size_t)nj * m[2]);
@@ -66,6 +82,7 @@ void sweep_stats(const uint32_t *tri, int64_t ntri, const float *x, const float 
                         cand[ncand++] = t;
                         if (dup) continue;
                         ++evals;
+                        { int exd = 0; for (int z = 0; z < n_ex; ++z) if (ex_t[z] == t) exd = 1; extra[4 * s + 3] += exd; }
                         {
                             const uint32_t *vv = tri + 3 * (size_t)t; int inb = 1;
                             for (int ax = 0; ax < 3; ++ax) {

@@ -37,7 +37,7 @@ print("  s  visits  stampact  evalnodes   evals  changes  rounds  actrounds  act
 for s in range(16):
     print("%3d" % s, " ".join("%9.0f" % (x / n_mesh) for x in tot[s]))
 print("sum", " ".join("%9.0f" % (x / n_mesh) for x in tot.sum(0)))
-print('in-band-box / seen-before / either:')
+print('in-band-box / seen-before / either / dup-of-examined-upwind:')
 for s in range(16):
     print('%3d' % s, ' '.join('%9.0f' % (x / n_mesh) for x in etot[s]))
 print('sum', ' '.join('%9.0f' % (x / n_mesh) for x in etot.sum(0)))
