@@ -684,41 +684,46 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 
 // ---- candidate selection of a sweep visit (shared by both sweep kernels) ----
-__device__ __forceinline__ int tri_of(uint32_t w) { return (w & kTriMask) != kTriMask ? (int)(w & kTriMask) : -1; }
-// bit r: the change code of neighbour r is not above the node's threshold for slot r (thw: the seven threshold bytes)
-__device__ __forceinline__ uint32_t examined_mask(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
-                                                  uint32_t w6, uint2 thw)
+// Thresholds of the current sweep as words: s_thrw[f][r] = (threshold code + 1) << 27, so that "the neighbour has not
+// changed since this node last examined it" is the unsigned comparison w < s_thrw (the change code sits in the top 5 bits
+// of a key's low word). Rebuilt by the first 64 threads at the start of every sweep (callers put a barrier behind it).
+__device__ __forceinline__ void sweep_threshold_words(const int8_t (*thr_s)[8], uint32_t (*thrw)[8])
 {
-#define G3D_THR(word, byte) ((int)(int8_t)((word) >> (8 * (byte))))
-    uint32_t xm = 0;
-    xm |= (int)(w0 >> 27) <= G3D_THR(thw.x, 0) ? 1u : 0u;
-    xm |= (int)(w1 >> 27) <= G3D_THR(thw.x, 1) ? 2u : 0u;
-    xm |= (int)(w2 >> 27) <= G3D_THR(thw.x, 2) ? 4u : 0u;
-    xm |= (int)(w3 >> 27) <= G3D_THR(thw.x, 3) ? 8u : 0u;
-    xm |= (int)(w4 >> 27) <= G3D_THR(thw.y, 0) ? 16u : 0u;
-    xm |= (int)(w5 >> 27) <= G3D_THR(thw.y, 1) ? 32u : 0u;
-    xm |= (int)(w6 >> 27) <= G3D_THR(thw.y, 2) ? 64u : 0u;
-#undef G3D_THR
-    return xm;
+    if (threadIdx.x < 64) thrw[threadIdx.x >> 3][threadIdx.x & 7] = (uint32_t)((int)thr_s[threadIdx.x >> 3][threadIdx.x & 7] + 1) << 27;
 }
-// Which candidates need an evaluation. A candidate cannot pass the strict `<` when it is the node's own triangle, an
+// Which of the 7 upwind neighbours (low words w[r] of their keys, thresholds tw[r]) need an evaluation; t[r] receives the
+// triangle fields. cm: the candidates -- neighbours that hold a triangle and have changed since they were last examined.
+// A candidate cannot pass the strict `<` when it is the node's own triangle (own: the triangle field of its key), an
 // earlier candidate of the same visit, or the triangle of ANY upwind neighbour that has not changed since the node last
 // examined it: the node met that triangle then (evaluated it, or skipped it for one of these very reasons), and phi has
 // only decreased since. The last case costs nothing to detect -- the seven words are loaded anyway -- and removes four
 // evaluations in ten (the same triangle reaching a node through a second neighbour).
-__device__ __forceinline__ uint32_t sweep_need_mask(const int (&a)[7], uint32_t xm, uint32_t cm, int ct)
+__device__ __forceinline__ uint32_t sweep_candidates(const uint32_t (&w)[7], const uint32_t (&tw)[7], uint32_t (&t)[7], uint32_t& xm)
 {
-    // one comparison per pair of slots: eq[q] bit r = slots q < r hold the same triangle. Then slot r is dropped (an earlier
+    uint32_t cm = 0;
+    xm = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        t[r] = w[r] & kTriMask;
+        const bool ex = w[r] < tw[r];
+        xm |= ex ? 1u << r : 0u;
+        cm |= (!ex && t[r] != kTriMask) ? 1u << r : 0u;
+    }
+    return cm;
+}
+__device__ __forceinline__ uint32_t sweep_need_mask(const uint32_t (&t)[7], uint32_t xm, uint32_t cm, uint32_t own)
+{
+    // one comparison per pair of slots: eq bit r = slots q < r hold the same triangle. Then slot r is dropped (an earlier
     // slot holds its triangle: a candidate evaluated first, or a neighbour examined before), and slot q is dropped when one
     // of its later twins is an examined neighbour. (Two empty slots compare equal too; they are no candidates anyway.)
     uint32_t drop = 0;
 #pragma unroll
-    for (int r = 0; r < 7; ++r) drop |= a[r] == ct ? 1u << r : 0u;
+    for (int r = 0; r < 7; ++r) drop |= t[r] == own ? 1u << r : 0u;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         uint32_t eq = 0;
 #pragma unroll
-        for (int r = q + 1; r < 7; ++r) eq |= a[q] == a[r] ? 1u << r : 0u;
+        for (int r = q + 1; r < 7; ++r) eq |= t[q] == t[r] ? 1u << r : 0u;
         drop |= eq;
         drop |= (eq & xm) ? 1u << q : 0u;
     }
@@ -737,7 +742,8 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     // at (-1: never). f = the axes on which the node lies on a grid face (bit 0: x ...): such a node is only part of the
     // sweeps that run towards its face, so for it an earlier sweep counts only if it ran the same way on those axes too.
     // In all: the last sweep that agrees with s on the axes of (r + 1) | f.
-    __shared__ __align__(8) int8_t s_thr[16][8][8];    // (r = 7: padding): a node fetches its seven thresholds in one load
+    __shared__ __align__(8) int8_t s_thr[16][8][8];    // (r = 7: padding)
+    __shared__ __align__(16) uint32_t s_thrw[8][8];    // the current sweep's thresholds as words, see sweep_threshold_words
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int R = sweep_rounds(NT);
@@ -786,6 +792,8 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
         sweep_dir(s, di, dj, dk);
         const int tmin = s_thr[s][7][6];            // the oldest threshold of the sweep: the last sweep in the same direction
         const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
+        sweep_threshold_words(s_thr[s], s_thrw);    // (the last level of the previous sweep ended with a barrier)
+        if (CL) cluster_barrier(); else __syncthreads();
         for (int L = 0; L < nlev; ++L) {
             // nothing upwind of this whole level has changed since it was last examined: every comparison the
             // reference would make here is known to fail. (Cluster variant: the table is per CTA, no skipping.)
@@ -810,22 +818,18 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     const int n0 = x1 + y0 + z0, n1 = x0 + y1 + z0, n2 = x1 + y1 + z0, n3 = x0 + y0 + z1,
                               n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
                     const int face = ((i == 0 || i == ni - 1) ? 1 : 0) | ((j == 0 || j == nj - 1) ? 2 : 0) | ((k == 0 || k == nk - 1) ? 4 : 0);
-                    const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][face][0]);   // bytes 0..3 | 4..6
-                    const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
-                                   w5 = Klo[2 * n5], w6 = Klo[2 * n6];
-                    // ta[r]: the neighbour's triangle (-1: none); xm bit r: the neighbour has not changed since this node last
-                    // examined it; cm bit r: it is a candidate
-                    const int ta[7] = { tri_of(w0), tri_of(w1), tri_of(w2), tri_of(w3), tri_of(w4), tri_of(w5), tri_of(w6) };
-                    const uint32_t xm = examined_mask(w0, w1, w2, w3, w4, w5, w6, thw);
-                    uint32_t cm = 0;
-#pragma unroll
-                    for (int r = 0; r < 7; ++r) cm |= (ta[r] >= 0 && !((xm >> r) & 1u)) ? 1u << r : 0u;
-                    c0 = ta[0]; c1 = ta[1]; c2 = ta[2]; c3 = ta[3]; c4 = ta[4]; c5 = ta[5]; c6 = ta[6];
+                    const uint4 tA = *reinterpret_cast<const uint4*>(&s_thrw[face][0]), tB = *reinterpret_cast<const uint4*>(&s_thrw[face][4]);
+                    const uint32_t tw[7] = { tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z };
+                    const uint32_t wd[7] = { Klo[2 * n0], Klo[2 * n1], Klo[2 * n2], Klo[2 * n3], Klo[2 * n4], Klo[2 * n5], Klo[2 * n6] };
+                    uint32_t tt[7], xm;
+                    const uint32_t cm = sweep_candidates(wd, tw, tt, xm);
+                    c0 = (int)tt[0]; c1 = (int)tt[1]; c2 = (int)tt[2]; c3 = (int)tt[3]; c4 = (int)tt[4]; c5 = (int)tt[5]; c6 = (int)tt[6];
                     if (cm) {                                            // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
                         phi = __uint_as_float((uint32_t)(kv >> 32));
-                        ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);
-                        need = sweep_need_mask(ta, xm, cm, ct);
+                        const uint32_t own = (uint32_t)kv & kTriMask;
+                        ct = own == kTriMask ? -1 : (int)own;
+                        need = sweep_need_mask(tt, xm, cm, own);
                     }
                 }
                 if (!__any_sync(0xffffffffu, need != 0)) return 0;
@@ -1032,6 +1036,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
     u64 n_eval = 0;
     extern __shared__ uint32_t s_mem[];
     __shared__ __align__(8) int8_t s_thr[16][8][8];    // as in tdf_sweep_kernel
+    __shared__ __align__(16) uint32_t s_thrw[8][8];
     __shared__ int s_nchg;                             // nodes changed in the sweep so far
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1126,22 +1131,18 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                     const int n0 = x1 + y0 + z0, n1 = x0 + y1 + z0, n2 = x1 + y1 + z0, n3 = x0 + y0 + z1,
                               n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
                     const int face = ((i == 0 || i == ni - 1) ? 1 : 0) | ((j == 0 || j == nj - 1) ? 2 : 0) | ((k == 0 || k == nk - 1) ? 4 : 0);
-                    const uint2 thw = *reinterpret_cast<const uint2*>(&s_thr[s][face][0]);   // bytes 0..3 | 4..6
-                    const uint32_t w0 = Klo[2 * n0], w1 = Klo[2 * n1], w2 = Klo[2 * n2], w3 = Klo[2 * n3], w4 = Klo[2 * n4],
-                                   w5 = Klo[2 * n5], w6 = Klo[2 * n6];
-                    // ta[r]: the neighbour's triangle (-1: none); xm bit r: the neighbour has not changed since this node last
-                    // examined it; cm bit r: it is a candidate
-                    const int ta[7] = { tri_of(w0), tri_of(w1), tri_of(w2), tri_of(w3), tri_of(w4), tri_of(w5), tri_of(w6) };
-                    const uint32_t xm = examined_mask(w0, w1, w2, w3, w4, w5, w6, thw);
-                    uint32_t cm = 0;
-#pragma unroll
-                    for (int r = 0; r < 7; ++r) cm |= (ta[r] >= 0 && !((xm >> r) & 1u)) ? 1u << r : 0u;
-                    c0 = ta[0]; c1 = ta[1]; c2 = ta[2]; c3 = ta[3]; c4 = ta[4]; c5 = ta[5]; c6 = ta[6];
+                    const uint4 tA = *reinterpret_cast<const uint4*>(&s_thrw[face][0]), tB = *reinterpret_cast<const uint4*>(&s_thrw[face][4]);
+                    const uint32_t tw[7] = { tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z };
+                    const uint32_t wd[7] = { Klo[2 * n0], Klo[2 * n1], Klo[2 * n2], Klo[2 * n3], Klo[2 * n4], Klo[2 * n5], Klo[2 * n6] };
+                    uint32_t tt[7], xm;
+                    const uint32_t cm = sweep_candidates(wd, tw, tt, xm);
+                    c0 = (int)tt[0]; c1 = (int)tt[1]; c2 = (int)tt[2]; c3 = (int)tt[3]; c4 = (int)tt[4]; c5 = (int)tt[5]; c6 = (int)tt[6];
                     if (cm) {                                            // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
                         phi = __uint_as_float((uint32_t)(kv >> 32));
-                        ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);
-                        need = sweep_need_mask(ta, xm, cm, ct);
+                        const uint32_t own = (uint32_t)kv & kTriMask;
+                        ct = own == kTriMask ? -1 : (int)own;
+                        need = sweep_need_mask(tt, xm, cm, own);
                     }
                 }
                 if (!__any_sync(0xffffffffu, need != 0)) return 0;
@@ -1280,6 +1281,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
         const int prev = s_nchg;
         // (spec_div < 0: always, from sweep 1 on -- tests)
         const bool spec = spec_div < 0 ? s >= 1 : (spec_div > 0 && s >= 8 && (int64_t)prev * spec_div <= (int64_t)n_lattice);
+        sweep_threshold_words(s_thr[s], s_thrw);
         __syncthreads();
         if (threadIdx.x == 0) s_nchg = 0;
         if (spec) sweep(std::true_type(), s); else sweep(std::false_type(), s);
