@@ -29,7 +29,7 @@
 // Exact mode (g3d_tdf_exact.cuh) shares prep and finalize and replaces init + sweeps by a culled brute force.
 //
 // HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B; keys u64 per mesh in 4x4x4 bricks
-// (hi = phi bits, lo = sweep change code << 27 | closest_tri; see KeyMap); parity bits u32 [n_mesh, ceil(nvox/32)];
+// (hi = phi bits, lo = sweep change code | band-box flags | closest_tri, see kTriBits; KeyMap); parity bits u32 [n_mesh, ceil(nvox/32)];
 // sweep order table (shared by all meshes).
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -45,7 +45,14 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr uint32_t kTriMask = 0x7ffffffu;           // low 27 bits of a key's low word: closest_tri (all ones = none)
+// Low word of a faithful-mode key: change code (4 bits: 0 = band init, s + 1 = sweep s, the last sweep shares 15 with the
+// one before -- nothing reads codes after it) | band-box flags (6 bits, see tdf_band_flags_kernel) | closest_tri (22 bits,
+// all ones = none). Exact-mode keys carry the plain triangle index.
+constexpr int kTriBits = 22, kFlagShift = 22, kCodeShift = 28;
+constexpr uint32_t kTriMask = (1u << kTriBits) - 1u;
+constexpr uint32_t kTriMaskExact = 0x7ffffffu;
+constexpr uint32_t kCodeMask = 0xfu << kCodeShift;
+__host__ __device__ inline uint32_t sweep_code(int s) { return (uint32_t)(s + 1 < 15 ? s + 1 : 15); }
 
 struct TdfWs {
     float4*   tri;          // 4 x float4 per triangle: TriRec (g3d_ptd.cuh)
@@ -198,8 +205,8 @@ tdf_prep_kernel(const float* __restrict__ verts, const int64_t* __restrict__ ver
     int m = mesh_of(tri_off, n_mesh, t);
     int64_t v0 = vert_off[m], nv = vert_off[m + 1] - v0;
     uint32_t ip = tris[3 * t], iq = tris[3 * t + 1], ir = tris[3 * t + 2];
-    // closest_tri is the mesh-local index in 27 bits: triangles of one mesh beyond that cannot be represented
-    const bool too_many = t - tri_off[m] >= (int64_t)kTriMask;
+    // closest_tri is the mesh-local index in 22 bits (27 in exact mode): triangles of one mesh beyond that cannot be represented
+    const bool too_many = t - tri_off[m] >= (int64_t)(P.mode == G3D_MODE_EXACT ? kTriMaskExact : kTriMask);
     if (too_many || ip >= nv || iq >= nv || ir >= nv) {
         // undefined behaviour in the reference (out-of-bounds read); flag the mesh
         // and neutralise the triangle: NaN vertices never win a `<` and an empty box
@@ -381,6 +388,18 @@ tdf_init_kernel(const float4* __restrict__ tri, const int4* __restrict__ box,
 // boxes (after clipping) are therefore walked one per LANE: 32 pending triangles at a time, each lane stepping
 // through the rows of its own box, one cull test per lane and step. Large boxes keep the
 // warp-wide walk. Survivors of both go to the same warp-private queue and are evaluated 32 at a time.
+// Band-box flags of the node (i, j, k) for a triangle with (clamped) band box b: does the box also hold the node's
+// neighbour at i+1, i-1, j+1, j-1, k+1, k-1 (bits 0..5). The band init evaluated the triangle at every node of its box, so
+// a sweep that finds the triangle at a neighbour of such a node need not evaluate it again there: the flags of the axes
+// the two nodes differ in say whether that node is inside the box (on the other axes it shares the flagged node's
+// coordinate, which is inside).
+__device__ __forceinline__ uint32_t band_flags(int4 b, int i, int j, int k)
+{
+    const int i0 = b.x & 0xffff, i1 = b.x >> 16, j0 = b.y & 0xffff, j1 = b.y >> 16, k0 = b.z & 0xffff, k1 = b.z >> 16;
+    return (i + 1 <= i1 ? 1u : 0u) | (i - 1 >= i0 ? 2u : 0u) | (j + 1 <= j1 ? 4u : 0u) | (j - 1 >= j0 ? 8u : 0u) |
+           (k + 1 <= k1 ? 16u : 0u) | (k - 1 >= k0 ? 32u : 0u);
+}
+
 constexpr int kTile = 16;
 constexpr int kLaneI = 8, kLaneRows = 64;            // lane-walked boxes: at most 8 wide in i, 64 (j, k) rows
 
@@ -587,9 +606,34 @@ tdf_init_tiled_kernel(const float4* __restrict__ tri, const int4* __restrict__ b
     u64* K = key + (int64_t)mesh * km.stride;
     for (int e = threadIdx.x; e < kTile * kTile * kTile; e += 256) {
         const int i = I0 + (e % kTile), j = J0 + (e / kTile) % kTile, k = K0 + e / (kTile * kTile);
-        if (i <= I1 && j <= J1 && k <= K1) K[kx(i) + ky(j, km.sbj) + kz(k, km.sbk)] = s_key[e];
+        if (i <= I1 && j <= J1 && k <= K1) {
+            u64 kv = s_key[e];
+            const uint32_t t = (uint32_t)kv;
+            if (t != 0xffffffffu) kv |= (u64)band_flags(__ldg(BX + t), i, j, k) << kFlagShift;
+            K[kx(i) + ky(j, km.sbj) + kz(k, km.sbk)] = kv;
+        }
     }
     if (counter && n_eval) atomicAdd(counter, n_eval);
+}
+
+// ------------------------------------------------------- band-box flags ----
+// The flags (see band_flags) for meshes [m0, m0 + n_mesh) after the scatter band init; the tiled one sets them as it
+// writes its block out.
+__global__ void __launch_bounds__(256)
+tdf_band_flags_kernel(u64* __restrict__ key, const int4* __restrict__ box, const int64_t* __restrict__ tri_off, int m0,
+                      int n_mesh, g3d_tdf_params P)
+{
+    const int64_t nvox = nvox_of(P);
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nvox * n_mesh) return;
+    const int mesh = m0 + (int)(q / nvox);
+    const int64_t v = q - (int64_t)(mesh - m0) * nvox;
+    const int i = (int)(v % P.ni), j = (int)((v / P.ni) % P.nj), k = (int)(v / ((int64_t)P.ni * P.nj));
+    const KeyMap km = keymap_of(P);
+    uint32_t* lo = reinterpret_cast<uint32_t*>(key + (int64_t)mesh * km.stride + (kx(i) + ky(j, km.sbj) + kz(k, km.sbk)));
+    const uint32_t w = *lo;
+    if (w == 0xffffffffu) return;                       // no triangle
+    *lo = w | (band_flags(__ldg(box + tri_off[mesh] + w), i, j, k) << kFlagShift);
 }
 
 // ----------------------------------------------------------- sweep order ----
@@ -684,28 +728,40 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 
 // ---- candidate selection of a sweep visit (shared by both sweep kernels) ----
-// Thresholds of the current sweep as words: s_thrw[f][r] = (threshold code + 1) << 27, so that "the neighbour has not
-// changed since this node last examined it" is the unsigned comparison w < s_thrw (the change code sits in the top 5 bits
-// of a key's low word). Rebuilt by the first 64 threads at the start of every sweep (callers put a barrier behind it).
-__device__ __forceinline__ void sweep_threshold_words(const int8_t (*thr_s)[8], uint32_t (*thrw)[8])
+// Thresholds of the current sweep as words: thrw[f][r] = (threshold code + 1) << kCodeShift, so that "the neighbour has not
+// changed since this node last examined it" is the unsigned comparison w < thrw (the change code sits in the top bits of a
+// key's low word). ib[r]: the band-box flags a neighbour at slot r must carry for this node to lie inside the band box of
+// the neighbour's triangle (the node is the neighbour's neighbour in the sweep direction on the axes of r + 1). Rebuilt by
+// the first threads of the CTA at the start of every sweep (callers put a barrier behind it).
+__device__ __forceinline__ void sweep_threshold_words(int s, const int8_t (*thr_s)[8], uint32_t (*thrw)[8], uint32_t* ib)
 {
-    if (threadIdx.x < 64) thrw[threadIdx.x >> 3][threadIdx.x & 7] = (uint32_t)((int)thr_s[threadIdx.x >> 3][threadIdx.x & 7] + 1) << 27;
+    if (threadIdx.x < 64) thrw[threadIdx.x >> 3][threadIdx.x & 7] = (uint32_t)((int)thr_s[threadIdx.x >> 3][threadIdx.x & 7] + 1) << kCodeShift;
+    if (threadIdx.x >= 64 && threadIdx.x < 72) {
+        int di, dj, dk;
+        sweep_dir(s, di, dj, dk);
+        const int a = (int)threadIdx.x - 63;            // 1..8 (8: padding)
+        const uint32_t f = ((a & 1) ? (di > 0 ? 1u : 2u) : 0u) | ((a & 2) ? (dj > 0 ? 4u : 8u) : 0u) | ((a & 4) ? (dk > 0 ? 16u : 32u) : 0u);
+        ib[a - 1] = a < 8 ? f << kFlagShift : 0xffffffffu;
+    }
 }
 // Which of the 7 upwind neighbours (low words w[r] of their keys, thresholds tw[r]) need an evaluation; t[r] receives the
-// triangle fields. cm: the candidates -- neighbours that hold a triangle and have changed since they were last examined.
+// triangle fields. cm: the candidates -- neighbours that hold a triangle the node has not met through them. A neighbour is
+// "met" (xm) when it has not changed since the node last examined it, or when it still holds its band-init triangle and
+// its flags say that this node lies inside that triangle's band box: the band init evaluated the pair.
 // A candidate cannot pass the strict `<` when it is the node's own triangle (own: the triangle field of its key), an
-// earlier candidate of the same visit, or the triangle of ANY upwind neighbour that has not changed since the node last
-// examined it: the node met that triangle then (evaluated it, or skipped it for one of these very reasons), and phi has
-// only decreased since. The last case costs nothing to detect -- the seven words are loaded anyway -- and removes four
-// evaluations in ten (the same triangle reaching a node through a second neighbour).
-__device__ __forceinline__ uint32_t sweep_candidates(const uint32_t (&w)[7], const uint32_t (&tw)[7], uint32_t (&t)[7], uint32_t& xm)
+// earlier candidate of the same visit, or the triangle of ANY met neighbour: the node met that triangle then (evaluated
+// it, or skipped it for one of these very reasons), and phi has only decreased since. The last case costs nothing to
+// detect -- the seven words are loaded anyway -- and removes four evaluations in ten (the same triangle reaching a node
+// through a second neighbour).
+__device__ __forceinline__ uint32_t sweep_candidates(const uint32_t (&w)[7], const uint32_t (&tw)[7], const uint32_t (&ib)[7],
+                                                     uint32_t (&t)[7], uint32_t& xm)
 {
     uint32_t cm = 0;
     xm = 0;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
         t[r] = w[r] & kTriMask;
-        const bool ex = w[r] < tw[r];
+        const bool ex = w[r] < tw[r] || (w[r] & (ib[r] | kCodeMask)) == ib[r];
         xm |= ex ? 1u << r : 0u;
         cm |= (!ex && t[r] != kTriMask) ? 1u << r : 0u;
     }
@@ -744,6 +800,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     // In all: the last sweep that agrees with s on the axes of (r + 1) | f.
     __shared__ __align__(8) int8_t s_thr[16][8][8];    // (r = 7: padding)
     __shared__ __align__(16) uint32_t s_thrw[8][8];    // the current sweep's thresholds as words, see sweep_threshold_words
+    __shared__ __align__(16) uint32_t s_ib[8];
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int R = sweep_rounds(NT);
@@ -792,7 +849,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
         sweep_dir(s, di, dj, dk);
         const int tmin = s_thr[s][7][6];            // the oldest threshold of the sweep: the last sweep in the same direction
         const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
-        sweep_threshold_words(s_thr[s], s_thrw);    // (the last level of the previous sweep ended with a barrier)
+        sweep_threshold_words(s, s_thr[s], s_thrw, s_ib);    // (the last level of the previous sweep ended with a barrier)
         if (CL) cluster_barrier(); else __syncthreads();
         for (int L = 0; L < nlev; ++L) {
             // nothing upwind of this whole level has changed since it was last examined: every comparison the
@@ -821,8 +878,10 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     const uint4 tA = *reinterpret_cast<const uint4*>(&s_thrw[face][0]), tB = *reinterpret_cast<const uint4*>(&s_thrw[face][4]);
                     const uint32_t tw[7] = { tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z };
                     const uint32_t wd[7] = { Klo[2 * n0], Klo[2 * n1], Klo[2 * n2], Klo[2 * n3], Klo[2 * n4], Klo[2 * n5], Klo[2 * n6] };
+                    const uint4 iA = *reinterpret_cast<const uint4*>(&s_ib[0]), iB = *reinterpret_cast<const uint4*>(&s_ib[4]);
+                    const uint32_t ib[7] = { iA.x, iA.y, iA.z, iA.w, iB.x, iB.y, iB.z };
                     uint32_t tt[7], xm;
-                    const uint32_t cm = sweep_candidates(wd, tw, tt, xm);
+                    const uint32_t cm = sweep_candidates(wd, tw, ib, tt, xm);
                     c0 = (int)tt[0]; c1 = (int)tt[1]; c2 = (int)tt[2]; c3 = (int)tt[3]; c4 = (int)tt[4]; c5 = (int)tt[5]; c6 = (int)tt[6];
                     if (cm) {                                            // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
@@ -862,7 +921,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                 }
                 if (changed) {
                     const uint8_t code = (uint8_t)(s + 1);
-                    K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)code << 27) | (uint32_t)ct;
+                    K[n] = ((u64)__float_as_uint(phi) << 32) | (sweep_code(s) << kCodeShift) | (uint32_t)ct;
                     if (!CL) {
                         // stamp the node's own level in every direction (codes only grow and all writers of a sweep
                         // write the same value)
@@ -1037,6 +1096,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
     extern __shared__ uint32_t s_mem[];
     __shared__ __align__(8) int8_t s_thr[16][8][8];    // as in tdf_sweep_kernel
     __shared__ __align__(16) uint32_t s_thrw[8][8];
+    __shared__ __align__(16) uint32_t s_ib[8];
     __shared__ int s_nchg;                             // nodes changed in the sweep so far
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1134,8 +1194,10 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                     const uint4 tA = *reinterpret_cast<const uint4*>(&s_thrw[face][0]), tB = *reinterpret_cast<const uint4*>(&s_thrw[face][4]);
                     const uint32_t tw[7] = { tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z };
                     const uint32_t wd[7] = { Klo[2 * n0], Klo[2 * n1], Klo[2 * n2], Klo[2 * n3], Klo[2 * n4], Klo[2 * n5], Klo[2 * n6] };
+                    const uint4 iA = *reinterpret_cast<const uint4*>(&s_ib[0]), iB = *reinterpret_cast<const uint4*>(&s_ib[4]);
+                    const uint32_t ib[7] = { iA.x, iA.y, iA.z, iA.w, iB.x, iB.y, iB.z };
                     uint32_t tt[7], xm;
-                    const uint32_t cm = sweep_candidates(wd, tw, tt, xm);
+                    const uint32_t cm = sweep_candidates(wd, tw, ib, tt, xm);
                     c0 = (int)tt[0]; c1 = (int)tt[1]; c2 = (int)tt[2]; c3 = (int)tt[3]; c4 = (int)tt[4]; c5 = (int)tt[5]; c6 = (int)tt[6];
                     if (cm) {                                            // some neighbour holds a triangle worth trying
                         u64 kv = K[n];
@@ -1185,7 +1247,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                         }
                     }
                 } else if (changed) {
-                    K[n] = ((u64)__float_as_uint(phi) << 32) | ((uint32_t)(s + 1) << 27) | (uint32_t)ct;
+                    K[n] = ((u64)__float_as_uint(phi) << 32) | (sweep_code(s) << kCodeShift) | (uint32_t)ct;
                     ++n_changed;
                     sweep_record_change<SP>(pos, s, di, dj, dk, ni, nj, nk, dstride, s_dirty, chg_code, s_act, s_lvcnt);
                 }
@@ -1281,7 +1343,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
         const int prev = s_nchg;
         // (spec_div < 0: always, from sweep 1 on -- tests)
         const bool spec = spec_div < 0 ? s >= 1 : (spec_div > 0 && s >= 8 && (int64_t)prev * spec_div <= (int64_t)n_lattice);
-        sweep_threshold_words(s_thr[s], s_thrw);
+        sweep_threshold_words(s, s_thr[s], s_thrw, s_ib);
         __syncthreads();
         if (threadIdx.x == 0) s_nchg = 0;
         if (spec) sweep(std::true_type(), s); else sweep(std::false_type(), s);
@@ -1334,7 +1396,8 @@ tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ pa
         if (valid) {
             u64 kv = K[bricked ? (int64_t)(kx(i) + kyz) : idx];
             float phi = __uint_as_float((uint32_t)(kv >> 32));
-            ct = (((uint32_t)kv & kTriMask) == kTriMask) ? -1 : (int)((uint32_t)kv & kTriMask);   // top 5 bits: sweep bookkeeping
+            const uint32_t tmask = bricked ? kTriMask : kTriMaskExact;                 // (bricked = faithful-mode keys)
+            ct = (((uint32_t)kv & tmask) == tmask) ? -1 : (int)((uint32_t)kv & tmask);
             if (inside) phi = -phi;
             sdf = mul(phi, P.out_scale);                                    // main.cpp:119
         }
@@ -1523,7 +1586,7 @@ int tdf_begin(int64_t total_verts, int64_t total_tris, int32_t n_mesh, const g3d
     int rc = tdf_validate(n_mesh, total_verts, total_tris, p);
     if (rc != G3D_OK) return rc;
     if (p.mode != G3D_MODE_FAITHFUL && p.mode != G3D_MODE_EXACT) { set_error("tdf: unknown mode %d", p.mode); return G3D_ERR_INVALID; }
-    // Per MESH the limit is 2^27 - 2 triangles (closest_tri shares a 32-bit word with 5 bits of bookkeeping; checked
+    // Per MESH the limit is 2^22 - 2 triangles, 2^27 - 2 in exact mode (closest_tri shares a 32-bit word with bookkeeping bits; checked
     // on the device, where the offsets live: G3D_MESH_TOO_MANY_TRIS). Per CALL the evaluation queues hold global
     // triangle numbers in 32 bits.
     if (total_tris >= ((int64_t)1 << 32) - 1) {
@@ -1600,9 +1663,12 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const void* tris
         if (use_tiled && (int64_t)(m1 - m0) * nbx * nby * nbz < (int64_t)INT_MAX)
             tdf_init_tiled_kernel<<<(unsigned)((int64_t)(m1 - m0) * nbx * nby * nbz), 256, 0, stream>>>(
                 w.tri, w.box, tri_off, m0, nbx, nby, nbz, p, w.key, far, prof_counters());
-        else
+        else {
             tdf_init_kernel<<<grid_for((t1 - t0) * 32, 256, sms * 32), 256, 0, stream>>>(
                 w.tri, w.box, tri_off, t0, t1, p, w.key, far, prof_counters());
+            const int64_t n_keys = (int64_t)(m1 - m0) * nvox_of(p);
+            tdf_band_flags_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, stream>>>(w.key, w.box, tri_off, m0, m1 - m0, p);
+        }
         prof_mark(ST_INIT, stream);
     }
     G3D_CUDA_TRY(cudaGetLastError());

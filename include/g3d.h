@@ -48,7 +48,7 @@ extern "C" {
 #define G3D_MESH_OK             0
 #define G3D_MESH_BAD_INDEX      1   /* a face references a vertex >= n_vert (UB in the reference) */
 #define G3D_MESH_EMPTY          2   /* no vertices or no faces (LoaderMesh.h:83 asserts) */
-#define G3D_MESH_TOO_MANY_TRIS  4   /* more than 2^27 - 2 triangles in ONE mesh: the surplus is ignored */
+#define G3D_MESH_TOO_MANY_TRIS  4   /* more than 2^22 - 2 (exact mode: 2^27 - 2) triangles in ONE mesh: the surplus is ignored */
 
 int         g3d_version(void);
 const char* g3d_last_error(void);
@@ -100,8 +100,9 @@ size_t g3d_tdf_workspace_bytes(int32_t n_mesh, int64_t total_verts, int64_t tota
  * tris      u32 [total_tris, 3]    vertex indices LOCAL to their mesh
  * tri_off   i64 [n_mesh + 1]       first triangle of each mesh
  * total_verts/total_tris repeat vert_off[n_mesh]/tri_off[n_mesh] so that the
- * host never has to read device memory. One MESH may hold at most 2^27 - 2 triangles
- * (closest_tri shares a 32-bit word with 5 bits of sweep bookkeeping; a larger mesh is
+ * host never has to read device memory. One MESH may hold at most 2^22 - 2 = 4,194,302
+ * triangles in faithful mode, 2^27 - 2 in exact mode (closest_tri shares a 32-bit word with
+ * 10 bits of sweep bookkeeping; a larger mesh is
  * flagged G3D_MESH_TOO_MANY_TRIS and its surplus triangles are ignored); one CALL at
  * most 2^32 - 2 in total (G3D_ERR_INVALID beyond; split the batch).
  */

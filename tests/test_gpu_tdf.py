@@ -314,7 +314,7 @@ def test_cabi_error_paths(g3d):
     assert L.g3d_tdf_batch(*args(need)) == -1
     p.ni = 32
     # the evaluation queues carry global triangle numbers in 32 bits: 2^32 - 1 triangles in one call are one too many
-    # (the per-MESH limit of 2^27 - 2 is enforced on the device: G3D_MESH_TOO_MANY_TRIS)
+    # (the per-MESH limit of 2^22 - 2, 2^27 - 2 in exact mode, is enforced on the device: G3D_MESH_TOO_MANY_TRIS)
     assert L.g3d_tdf_batch(v.data_ptr(), off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), (1 << 32) - 1, 1, C.byref(p),
                            C.byref(o), ws.data_ptr(), need, None) == -1 and b"triangles" in L.g3d_last_error()
     assert L.g3d_tdf_batch(v.data_ptr(), off.data_ptr(), 3, t.data_ptr(), toff.data_ptr(), (1 << 27) + 5, 1, C.byref(p),

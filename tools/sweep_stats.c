@@ -14,7 +14,7 @@ static void sdir(int s, int *d)
 /* out[s][0..7]: visits, stamp-active nodes, nodes with >= 1 evaluation, evaluations, changes,
  *               32-node rounds in all levels, rounds holding a stamp-active node, levels holding one */
 void sweep_stats(const uint32_t *tri, int64_t ntri, const float *x, const float *origin, float dx, int ni, int nj,
-                 int nk, int64_t *out, int64_t *extra, int64_t *extra2)
+                 int nk, int64_t *out, int64_t *extra, int64_t *extra2, int64_t *extra3)
 {
     /* extra[s][0]: evals with n inside band box of t; [1]: evals of a pair evaluated in an earlier sweep; [2]: either */
     uint64_t *hist = (uint64_t *)calloc((size_t)ni * nj * nk * 64, 8); int *hn = (int *)calloc((size_t)ni * nj * nk, 4);
@@ -82,7 +82,25 @@ void sweep_stats(const uint32_t *tri, int64_t ntri, const float *x, const float 
                         cand[ncand++] = t;
                         if (dup) continue;
                         ++evals;
-                        { int exd = 0; for (int z = 0; z < n_ex; ++z) if (ex_t[z] == t) exd = 1; extra[4 * s + 3] += exd; }
+                        { int exd = 0; for (int z = 0; z < n_ex; ++z) if (ex_t[z] == t) exd = 1; extra[4 * s + 3] += exd;
+                          if (!exd) {
+                            /* m = neighbour qm holds t; flags only valid if stamp[qm] == 0 (init-assigned) */
+                            const uint32_t *vv = tri + 3 * (size_t)t; int inb = 1, interior = 1, dirok = 1;
+                            for (int ax = 0; ax < 3; ++ax) {
+                                double f0 = ((double)x[3*vv[0]+ax] - origin[ax]) / dx, f1 = ((double)x[3*vv[1]+ax] - origin[ax]) / dx, f2 = ((double)x[3*vv[2]+ax] - origin[ax]) / dx;
+                                int lo = clamp_i((int)min3_d(f0, f1, f2) - 1, 0, dims[ax] - 1), hi = clamp_i((int)max3_d(f0, f1, f2) + 2, 0, dims[ax] - 1);
+                                if (p[ax] < lo || p[ax] > hi) inb = 0;
+                                if (!(m[ax] > lo && m[ax] < hi)) interior = 0;
+                                if (p[ax] != m[ax] && (p[ax] < lo || p[ax] > hi)) dirok = 0;
+                            }
+                            int init_assigned = stamp[qm] == 0;
+                            extra2[8 * s + 7] += 1;                                   /* evals left after dup rule */
+                            extra[4 * s + 0] += 0;
+                            extra3[4 * s + 0] += inb;                                  /* full in-band knowledge */
+                            extra3[4 * s + 1] += (init_assigned && interior);          /* 1-bit flag */
+                            extra3[4 * s + 2] += (init_assigned && dirok);             /* 6-bit flags */
+                          }
+                        }
                         {
                             const uint32_t *vv = tri + 3 * (size_t)t; int inb = 1;
                             for (int ax = 0; ax < 3; ++ax) {
