@@ -815,6 +815,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     // per level.
     const int dstride = nlev + 3;
     uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev + 3]
+    uint32_t* s_lut = s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue) + (8 * dstride + 3) / 4;       // [na + nb + nc]
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
     for (int l = threadIdx.x; l < 8 * dstride; l += NT) s_dirty[l] = 0;
     for (int e = threadIdx.x; e < 16 * 8 * 8; e += NT) {
@@ -840,7 +841,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
     // 4-byte load tells both whether a neighbour needs to be examined and which triangle it holds
     const uint32_t* Klo = (const uint32_t*)K;
     const float4* T = tri + 4 * tri_off[mesh];
-    const int ni = P.ni, nj = P.nj, nk = P.nk;
+    const int ni = P.ni, nj = P.nj, nk = P.nk, na = ni - 1, nb = nj - 1, nc = nk - 1;
 
     // chg (optional): per-code change bitmaps of the mesh for tdf_sweep_bm_kernel, which takes over the later sweeps
     uint32_t* const Cm = chg ? chg + (int64_t)mesh * 17 * act_words : nullptr;
@@ -850,6 +851,18 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
         const int tmin = s_thr[s][7][6];            // the oldest threshold of the sweep: the last sweep in the same direction
         const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
         sweep_threshold_words(s, s_thr[s], s_thrw, s_ib);    // (the last level of the previous sweep ended with a barrier)
+        // per sweep-relative coordinate: key offset of the node | upwind neighbour in another brick << 30 | grid face << 31
+        for (int e = threadIdx.x; e < na + nb + nc; e += NT) {
+            const int ax = e < na ? 0 : (e < na + nb ? 1 : 2), rel = e - (ax == 0 ? 0 : (ax == 1 ? na : na + nb));
+            const int d = ax == 0 ? di : (ax == 1 ? dj : dk), nn = ax == 0 ? ni : (ax == 1 ? nj : nk);
+            const int v = d > 0 ? 1 + rel : nn - 2 - rel;
+            const int off = ax == 0 ? kx(v) : (ax == 1 ? ky(v, km.sbj) : kz(v, km.sbk));
+            const bool cross = d > 0 ? (v & 3) == 0 : (v & 3) == 3, face = v == 0 || v == nn - 1;
+            s_lut[e] = (uint32_t)off | (cross ? 0x40000000u : 0u) | (face ? 0x80000000u : 0u);
+        }
+        // key steps to the upwind neighbour inside a brick / across bricks, and the node of sweep-relative coordinate 0
+        const int3 step = make_int3(di, 4 * dj, 16 * dk), stepc = make_int3(61 * di, (km.sbj - 12) * dj, (km.sbk - 48) * dk);
+        const int3 base = make_int3(di > 0 ? 1 : ni - 2, dj > 0 ? 1 : nj - 2, dk > 0 ? 1 : nk - 2);
         if (CL) cluster_barrier(); else __syncthreads();
         for (int L = 0; L < nlev; ++L) {
             // nothing upwind of this whole level has changed since it was last examined: every comparison the
@@ -862,19 +875,18 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                 int c0 = -1, c1 = -1, c2 = -1, c3 = -1, c4 = -1, c5 = -1, c6 = -1;
                 need = 0; pos = 0; phi = 0.f; ct = -1; n = 0; off = 0;
                 if (q < end) {
-                    uint32_t o = __ldg(order + q);
-                    int a = o & 1023, b = (o >> 10) & 1023, c = o >> 20;
-                    int i = di > 0 ? 1 + a : ni - 2 - a;
-                    int j = dj > 0 ? 1 + b : nj - 2 - b;
-                    int k = dk > 0 ? 1 + c : nk - 2 - c;
-                    pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+                    // the node is known by its sweep-relative coordinates (pos = a | b << 10 | c << 20); key offsets, brick
+                    // crossings and grid faces per coordinate come from the sweep's tables
+                    pos = __ldg(order + q);
+                    const uint32_t lx = s_lut[pos & 1023u], ly = s_lut[na + ((pos >> 10) & 1023u)], lz = s_lut[na + nb + (pos >> 20)];
                     // the node and its 7 upwind neighbours (in the order of cpp:72-78) in the bricked key layout
-                    const int x0 = kx(i), x1 = kx(i - di), y0 = ky(j, km.sbj), y1 = ky(j - dj, km.sbj),
-                              z0 = kz(k, km.sbk), z1 = kz(k - dk, km.sbk);
+                    const int x0 = (int)(lx & 0x3fffffffu), y0 = (int)(ly & 0x3fffffffu), z0 = (int)(lz & 0x3fffffffu);
+                    const int x1 = x0 - ((lx & 0x40000000u) ? stepc.x : step.x), y1 = y0 - ((ly & 0x40000000u) ? stepc.y : step.y),
+                              z1 = z0 - ((lz & 0x40000000u) ? stepc.z : step.z);
                     n = x0 + y0 + z0;
                     const int n0 = x1 + y0 + z0, n1 = x0 + y1 + z0, n2 = x1 + y1 + z0, n3 = x0 + y0 + z1,
                               n4 = x1 + y0 + z1, n5 = x0 + y1 + z1, n6 = x1 + y1 + z1;
-                    const int face = ((i == 0 || i == ni - 1) ? 1 : 0) | ((j == 0 || j == nj - 1) ? 2 : 0) | ((k == 0 || k == nk - 1) ? 4 : 0);
+                    const int face = (int)((lx >> 31) | ((ly >> 31) << 1) | ((lz >> 31) << 2));
                     const uint4 tA = *reinterpret_cast<const uint4*>(&s_thrw[face][0]), tB = *reinterpret_cast<const uint4*>(&s_thrw[face][4]);
                     const uint32_t tw[7] = { tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z };
                     const uint32_t wd[7] = { Klo[2 * n0], Klo[2 * n1], Klo[2 * n2], Klo[2 * n3], Klo[2 * n4], Klo[2 * n5], Klo[2 * n6] };
@@ -925,7 +937,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     if (!CL) {
                         // stamp the node's own level in every direction (codes only grow and all writers of a sweep
                         // write the same value)
-                        const int pi = (int)(pos & 1023u), pj = (int)((pos >> 10) & 1023u), pk = (int)(pos >> 20);
+                        const int pi = base.x + di * (int)(pos & 1023u), pj = base.y + dj * (int)((pos >> 10) & 1023u), pk = base.z + dk * (int)(pos >> 20);
 #pragma unroll
                         for (int dq = 0; dq < 8; ++dq) {
                             int ei, ej, ek;
@@ -953,7 +965,7 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                 __syncwarp();
                 for (int e = lane; e < W; e += 32) {
                     uint32_t pp = q_pos[e];
-                    V3 gx = node_pos((int)(pp & 1023u), (int)((pp >> 10) & 1023u), (int)(pp >> 20), P);
+                    V3 gx = node_pos(base.x + di * (int)(pp & 1023u), base.y + dj * (int)((pp >> 10) & 1023u), base.z + dk * (int)(pp >> 20), P);
                     q_pos[e] = __float_as_uint(point_triangle_distance(gx, load_trirec(T + 4 * (int64_t)q_tri[e])));
                     ++n_eval;
                 }
@@ -1463,7 +1475,8 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
 {
     s_end = min(s_end, sweep_count_env());
     const int lev_words = (nlev + 1 + 3) & ~3;
-    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue) * 4 + (size_t)8 * (nlev + 3);
+    const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue + (8 * (nlev + 3) + 3) / 4 +
+                                 (p.ni - 1) + (p.nj - 1) + (p.nk - 1)) * 4;
     auto kern = tdf_sweep_kernel<NT, CL>;
     G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
