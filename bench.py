@@ -330,7 +330,8 @@ def bench_other_configs(args, rank, world, dev, barrier, peak_tf, nominal_tf):
                                        "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
                                        "frac_of_nominal": ach / nominal_tf, "evals_per_launch": dom_evals,
                                        "kernel_ms": st.get(dom), "traffic": None}}
-            launches += (6 if mode == "faithful" else 7) * (steps + warm + 1)
+            # faithful: fill, prep, band init, order, sweep (two kernels on grids the small-grid kernel takes), finalize
+            launches += (7 if (mode == "exact" or dim ** 3 <= 65536) else 6) * (steps + warm + 1)
             keep[mode] = o["sdf"][0].clone()
             assert int(o["status"].sum().item()) == 0
         return case, (v, t, keep)
@@ -365,7 +366,7 @@ def bench_other_configs(args, rank, world, dev, barrier, peak_tf, nominal_tf):
         "value_incl_generation": total * DIM ** 3 / (ms_all * 1e-3), "total_ms": ms_all,
         "resident_output_gb": sum(v.numel() * v.element_size() for v in shard_out.values()) / 1e9,
         "models_with_error_flags": bad}
-    launches += 6 * (tm["chunks"] + 1)
+    launches += 7 * (tm["chunks"] + 1)
     del shard_out
     return res, launches, (k0, k3)
 
@@ -430,7 +431,8 @@ def run_b200(args, rank, world, local):
     stage /= args.steps
     total_vox = shard.all_reduce_sum(M * DIM ** 3, dev)
     value = total_vox / (ms_step * 1e-3)
-    tdf_launches = 6 * args.steps if args.mode == "faithful" else 7 * args.steps
+    # per step: fill, prep, band init, order, 2 sweep kernels, finalize (exact: fill, prep, 3 index kernels, exact, finalize)
+    tdf_launches = 7 * args.steps
 
     names = ["fill", "prep", "band_init", "order", "sweep", "finalize", "exact", "raycast"]
     stages_ms = {n: round(float(s), 4) for n, s in zip(names, stage) if s > 0}
@@ -443,15 +445,22 @@ def run_b200(args, rank, world, local):
     nominal = props.multi_processor_count * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     achieved = (exact_flops(evals) if args.mode == "exact" else FLOP_PER_EVAL * dom_evals) / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
     roofline = {
-        "kernel": "tdf_sweep_kernel" if args.mode == "faithful" else "tdf_exact3_kernel", "bound": "fp32",
+        "kernel": "tdf_sweep_kernel + tdf_sweep_bm_kernel (first / second pass of the 16 sweeps)" if args.mode == "faithful" else "tdf_exact3_kernel", "bound": "fp32",
         "achieved": achieved, "peak": float(tf.value), "unit": "TFLOP/s", "frac": achieved / float(tf.value) if tf.value else None,
         "peak_source": "on-box FFMA probe (g3d_probe_fp32_tflops); MEASURED_PEAKS.json has no FP32 figure",
         "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
         "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": dom_evals, "kernel_ms": dom_ms,
-        "note": "faithful arithmetic issues no FMA (bit parity with the CPU reference), so 0.5 of the FMA peak is its ceiling",
+        "note": "faithful arithmetic issues no FMA (bit parity with the CPU reference), so 0.5 of the FMA peak is its ceiling; "
+                "only evaluations actually performed count: the kernel gets its speed from proving evaluations unnecessary, which "
+                "LOWERS this fraction (round 1: 4.0e8 evaluations per launch, now 1.8e8 in less time)",
         "traffic": None,
     }
-    tt = traffic_table().get(roofline["kernel"])
+    if args.mode == "faithful":
+        # for scale: the evaluations the reference makes in its 16 sweeps (7 per node and sweep, cpp:57-80), at the same 76 FLOP
+        ref_evals = 112 * (DIM - 1) ** 3 * M
+        roofline["reference_sweep_evals_per_launch"] = ref_evals
+        roofline["achieved_reference_equivalent"] = FLOP_PER_EVAL * ref_evals / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
+    tt = traffic_table().get("tdf_sweep_kernel" if args.mode == "faithful" else roofline["kernel"])
     if tt and M == 1024 and args.n == 18:
         roofline["traffic"] = tt["bytes_per_launch"]
         roofline["traffic_source"] = tt["source"] + " (ncu --set full, same workload)"
@@ -502,7 +511,7 @@ def run_b200(args, rank, world, local):
                                            "(1.8e8 ratings per step against 6.5e11 pairs for a brute force), and the kernel is bound by instruction "
                                            "issue of the index walk (ncu: " + str(traffic_table().get("tdf_exact3_kernel", {}).get("issue_active_pct", "n/a")) +
                                            " % issue-active, fma pipe " + str(traffic_table().get("tdf_exact3_kernel", {}).get("fma_pipe_pct", "n/a")) + " %)"}}
-        tdf_launches += (7 if other == "exact" else 6) * (nst + 2)
+        tdf_launches += 7 * (nst + 2)
         del oo
 
     # ---- the other BASELINE configs: [0] one 5k-tri mesh, [3] 128^3 x 200k tris, [4] the 100k-model data set
@@ -737,8 +746,8 @@ def run_b200(args, rank, world, local):
                         "api": "g3d_tdf_batch_host (32-bit indices), one call per step, returns when the results are on the host"},
                "numa_bind": numa}
         L.g3d_context_destroy(ctx)
-        # per host-path step: fill, 4 x (prep, band init), order, sweep, 4 x finalize (exact: fill, 4 x prep, exact, 4 x finalize)
-        tdf_launches += 2 * args.steps * (15 if args.mode == "faithful" else 10)
+        # per host-path step: fill, 4 x (prep, band init), order, 2 sweep kernels, 4 x finalize (exact: fill, 4 x prep, 3 index kernels, exact, 4 x finalize)
+        tdf_launches += 2 * args.steps * (16 if args.mode == "faithful" else 13)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's make_level_set3, one thread
     cpu = None
