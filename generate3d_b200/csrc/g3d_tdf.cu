@@ -1146,6 +1146,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
     const float4* T = tri + 4 * tri_off[mesh];
     const int ni = P.ni, nj = P.nj, nk = P.nk;
     const int n_lattice = (ni - 1) * (nj - 1) * (nk - 1);
+    const float rcp_ni = 1.0f / (float)ni, rcp_nj = 1.0f / (float)nj;
     // change bitmaps of this mesh, one per code (0 = the band init, s + 1 = sweep s), zero at launch
     uint32_t* Cm = chg + (int64_t)mesh * 17 * act_words;
     __syncthreads();
@@ -1265,6 +1266,8 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                 }
             };
             int ln = 0;                                 // SP: nodes waiting in s_list (warp-uniform)
+            int fnext = warp * 32, fidx = 0;            // flat visit: next chunk of bitmap words, this lane's word
+            uint32_t fword = 0u;                        //             and what is left of it
             for (int qb = beg + warp * 32; ; qb += R * NT) {
                 bool vA = false, vB = false, kp0 = false, kp1 = false;
                 uint32_t posA = 0, posB = 0, keep0 = 0, keep1 = 0;
@@ -1284,9 +1287,39 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                     // scan R rounds against the activity bits. Where most nodes are active they go straight on; otherwise
                     // the active ones collect in s_list and a batch runs when 32 R are waiting, or with what is left once
                     // the range has been scanned
-                    const bool more = qb < end;
+                    bool more = qb < end;
                     bool direct = false;
-                    if (more) {
+                    if (flat) {
+                        // the speculative visit takes the marked nodes straight from the bitmap: a warp holds 32 words at a
+                        // time, every lane hands over the lowest bit of its word per step (the order of the visit is free)
+                        more = true;
+                        if (!__any_sync(0xffffffffu, fword != 0u)) {
+                            if (fnext < act_words) {
+                                fidx = fnext + lane;
+                                fword = fidx < act_words ? s_act[fidx] : 0u;
+                                fnext += NT;
+                                continue;
+                            }
+                            more = false;
+                            if (ln == 0) break;
+                        } else {
+                            vA = fword != 0u;
+                            if (vA) {
+                                const int p = 32 * fidx + __ffs(fword) - 1;
+                                fword &= fword - 1u;
+                                // (p < 65,536: the float quotients are exact, as in the band init's box walk)
+                                const int r = (int)(((float)p + 0.5f) * rcp_ni), k = (int)(((float)r + 0.5f) * rcp_nj);
+                                const int i = p - r * ni, j = r - k * nj;
+                                posA = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
+                                // bits of nodes outside this sweep's lattice (grid faces, tail of the last word) are not nodes to visit
+                                vA = k < nk && (di > 0 ? i >= 1 : i <= ni - 2) && (dj > 0 ? j >= 1 : j <= nj - 2) && (dk > 0 ? k >= 1 : k <= nk - 2);
+                            }
+                            const uint32_t m0 = __ballot_sync(0xffffffffu, vA);
+                            if (vA) s_list[ln + __popc(m0 & lt)] = posA;
+                            ln += __popc(m0);
+                            if (ln < 32 * R) continue;
+                        }
+                    } else if (more) {
                         vA = node_at(qb + lane, posA);
                         if (R == 2) vB = node_at(qb + NT + lane, posB);
                         const uint32_t m0 = __ballot_sync(0xffffffffu, vA), m1 = R == 2 ? __ballot_sync(0xffffffffu, vB) : 0u;
