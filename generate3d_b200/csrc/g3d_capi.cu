@@ -379,7 +379,9 @@ static int tdf_host_submit(g3d_context* c, const float* verts, const int64_t* ve
     // still running into the caller's arrays (or the arena) after the call has reported an error
     auto bail = [&](int code) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(c->s_out); return code; };
 #define G3D_TRY_BAIL(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(g3d::cuda_fail(e__, #expr)); } while (0)
-    const int nch = n_mesh >= 64 ? kHostChunks : 1;
+    // (with the other slot's batch still in flight this batch's copies hide behind that one's kernels anyway: no chunks then,
+    // whole-batch launches fill the GPU better -- 4 chunks cost the 1,024-mesh step 1.5 ms in partial waves)
+    const int nch = (n_mesh >= 64 && !c->busy[slot ^ 1]) ? kHostChunks : 1;
     auto chunk_lo = [&](int ch) { return (int)((int64_t)n_mesh * ch / nch); };
     G3D_TRY_BAIL(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
     G3D_TRY_BAIL(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
