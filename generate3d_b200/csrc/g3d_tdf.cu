@@ -1692,12 +1692,15 @@ int tdf_stage_tris(const float* verts, const int64_t* vert_off, const void* tris
         prof_mark(ST_PREP, stream);
     } else {
         TdfWs w = carve(ws, n_mesh, total_tris, p);
-        if (index_bytes == 2)
-            tdf_prep_kernel<uint16_t, 3><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
-                verts, vert_off, (const uint16_t*)tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr);
-        else
-            tdf_prep_kernel<uint32_t, 3><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>(
-                verts, vert_off, (const uint32_t*)tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr);
+        // resident CTAs per SM the kernel is compiled for: 4 (64 registers) measured 0.72 ms per 1,024 meshes, 3 (76): 0.78,
+        // 6 (40, spills): 0.76 -- the kernel waits on its vertex gathers. G3D_PREP_MINB overrides (tuning aid).
+        const char* e_pb = getenv("G3D_PREP_MINB");
+        const int pb = e_pb ? atoi(e_pb) : 4;
+#define G3D_PREP_F(IT, MB) tdf_prep_kernel<IT, MB><<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, stream>>>( \
+            verts, vert_off, (const IT*)tris, tri_off, t0, t1, n_mesh, p, w.tri, w.box, w.parity, out.status, nullptr, nullptr, nullptr, nullptr)
+        if (index_bytes == 2) { if (pb >= 6) G3D_PREP_F(uint16_t, 6); else if (pb >= 4) G3D_PREP_F(uint16_t, 4); else G3D_PREP_F(uint16_t, 3); }
+        else { if (pb >= 6) G3D_PREP_F(uint32_t, 6); else if (pb >= 4) G3D_PREP_F(uint32_t, 4); else G3D_PREP_F(uint32_t, 3); }
+#undef G3D_PREP_F
         prof_mark(ST_PREP, stream);
         // [t0, t1) are the triangles of meshes [m0, m1). Batches of small grids: one CTA per 16^3 block of a mesh, keys in
         // shared memory; each block scans all band boxes of its mesh, so big grids keep the scatter kernel, and so do
