@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "g3d_internal.h"
 
 namespace g3d {
@@ -104,6 +106,14 @@ struct g3d_context {
     cudaEvent_t ev_fin[2][kHostChunks] = {};        // chunk finalised, results may leave
     cudaEvent_t ev_done[2] = {};                    // all results of the slot's batch are on the host
     bool busy[2] = { false, false };
+    // did the kernel stream wait for inputs? Timed events around the kernels of the last four submissions: a batch whose
+    // first kernel could only start some time after the previous batch's last one had ended found the GPU idle, i.e. the
+    // host side (PCIe, host memory shared with other ranks) is the slower party. Pipelined submissions are then cut into
+    // chunks, whose kernels can start on the first chunk; otherwise they go whole (fuller launches).
+    cudaEvent_t ev_kbeg[4] = {}, ev_kend[4] = {};
+    unsigned seq = 0;                               // submissions so far
+    unsigned seq_of[2] = { 0, 0 };                  // submission number of the batch in each slot
+    bool starved = false;
     char* arena[2] = { nullptr, nullptr };
     size_t arena_bytes[2] = { 0, 0 };
 };
@@ -293,6 +303,10 @@ int g3d_context_create(int32_t device, g3d_context** ctx)
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming);
     }
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+        e = cudaEventCreate(&c->ev_kbeg[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&c->ev_kend[i]);
+    }
     if (e != cudaSuccess) { g3d_context_destroy(c); return cuda_fail(e, "cudaStreamCreate/cudaEventCreate"); }
     *ctx = c;
     return G3D_OK;
@@ -313,6 +327,10 @@ void g3d_context_destroy(g3d_context* c)
         }
         if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]);
         if (c->arena[b]) cudaFreeAsync(c->arena[b], nullptr);
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (c->ev_kbeg[i]) cudaEventDestroy(c->ev_kbeg[i]);
+        if (c->ev_kend[i]) cudaEventDestroy(c->ev_kend[i]);
     }
     delete c;
 }
@@ -381,7 +399,9 @@ static int tdf_host_submit(g3d_context* c, const float* verts, const int64_t* ve
 #define G3D_TRY_BAIL(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(g3d::cuda_fail(e__, #expr)); } while (0)
     // (with the other slot's batch still in flight this batch's copies hide behind that one's kernels anyway: no chunks then,
     // whole-batch launches fill the GPU better -- 4 chunks cost the 1,024-mesh step 1.5 ms in partial waves)
-    const int nch = (n_mesh >= 64 && !c->busy[slot ^ 1]) ? kHostChunks : 1;
+    const char* e_ch = getenv("G3D_HOST_CHUNKS");               // tuning aid: 1 = always in chunks, 0 = never
+    const bool chunked = e_ch ? atoi(e_ch) != 0 : (!c->busy[slot ^ 1] || c->starved);
+    const int nch = (n_mesh >= 64 && chunked) ? kHostChunks : 1;
     auto chunk_lo = [&](int ch) { return (int)((int64_t)n_mesh * ch / nch); };
     G3D_TRY_BAIL(cudaMemcpyAsync(dvo, vert_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
     G3D_TRY_BAIL(cudaMemcpyAsync(dto, tri_off, (size_t)(n_mesh + 1) * 8, cudaMemcpyHostToDevice, c->s_in));
@@ -394,6 +414,9 @@ static int tdf_host_submit(g3d_context* c, const float* verts, const int64_t* ve
         G3D_TRY_BAIL(cudaEventRecord(ev_in[ch], c->s_in));
     }
     G3D_TRY_BAIL(cudaStreamWaitEvent(s, ev_in[0], 0));           // the offset arrays precede chunk 0 on the input stream
+    const unsigned seq = c->seq++;
+    c->seq_of[slot] = seq;
+    G3D_TRY_BAIL(cudaEventRecord(c->ev_kbeg[seq & 3], s));       // the kernel stream has its first inputs (and is done with the batch before)
     int rc = tdf_begin(nv, nt, n_mesh, *params, d, ws, ws_bytes, s);
     if (rc != G3D_OK) return bail(rc);
     for (int ch = 0; ch < nch; ++ch) {
@@ -419,6 +442,7 @@ static int tdf_host_submit(g3d_context* c, const float* verts, const int64_t* ve
         if (out->occ_f32) G3D_TRY_BAIL(cudaMemcpyAsync(out->occ_f32 + go, d.occ_f32 + go, gb, cudaMemcpyDeviceToHost, c->s_out));
         if (out->closest_tri) G3D_TRY_BAIL(cudaMemcpyAsync(out->closest_tri + go, d.closest_tri + go, gb, cudaMemcpyDeviceToHost, c->s_out));
     }
+    G3D_TRY_BAIL(cudaEventRecord(c->ev_kend[seq & 3], s));
     if (out->status) G3D_TRY_BAIL(cudaMemcpyAsync(out->status, d.status, (size_t)n_mesh * 4, cudaMemcpyDeviceToHost, c->s_out));
     G3D_TRY_BAIL(cudaEventRecord(c->ev_done[slot], c->s_out));
     c->busy[slot] = true;
@@ -454,6 +478,13 @@ int g3d_tdf_batch_host_wait(g3d_context* c, int32_t ticket)
     c->busy[ticket] = false;
     G3D_CUDA_TRY(cudaEventSynchronize(c->ev_done[ticket]));
     G3D_CUDA_TRY(cudaGetLastError());
+    // (both events lie behind this batch's results on the kernel stream; the ring keeps four submissions apart)
+    const unsigned seq = c->seq_of[ticket];
+    if (seq > 0 && c->seq - seq < 3) {
+        float gap_ms = 0.f;
+        if (cudaEventElapsedTime(&gap_ms, c->ev_kend[(seq - 1) & 3], c->ev_kbeg[seq & 3]) == cudaSuccess) c->starved = gap_ms > 0.25f;
+        else cudaGetLastError();
+    }
     return G3D_OK;
 }
 
