@@ -1495,18 +1495,10 @@ int grid_for(int64_t n, int block, int max_blocks)
 }  // namespace
 
 namespace {
-// timing aid only: fewer than the reference's 16 sweeps
-inline int sweep_count_env()
-{
-    const char* e_ns = getenv("G3D_SWEEP_COUNT");
-    return e_ns ? atoi(e_ns) : 16;
-}
-
 template <int NT, bool CL>
 int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p,
                     u64* cnt, cudaStream_t stream, int s_begin = 0, int s_end = 16, uint32_t* chg = nullptr)
 {
-    s_end = min(s_end, sweep_count_env());
     const int lev_words = (nlev + 1 + 3) & ~3;
     const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue + (8 * (nlev + 3) + 3) / 4 +
                                  (p.ni - 1) + (p.nj - 1) + (p.nk - 1)) * 4;
@@ -1544,7 +1536,7 @@ int launch_sweep_bm(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off
     const int spec_div = e_sp ? atoi(e_sp) : 8;
     kern<<<(unsigned)n_mesh, NT, smem, stream>>>(w.key, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
                                                  (const int32_t*)w.level_start, nlev, lev_words, p, cnt, w.chg,
-                                                 (const uint32_t*)w.bnd, w.act_words, s_begin, min(16, sweep_count_env()), spec_div);
+                                                 (const uint32_t*)w.bnd, w.act_words, s_begin, 16, spec_div);
     return G3D_OK;
 }
 
