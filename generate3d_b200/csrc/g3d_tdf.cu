@@ -1413,13 +1413,15 @@ tdf_finalize_kernel(const u64* __restrict__ key, const uint32_t* __restrict__ pa
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (mesh - mesh0, k, j)
     int64_t nrow = (int64_t)n_mesh * P.nk * P.nj;
     if (row >= nrow) return;
-    row += (int64_t)mesh0 * P.nk * P.nj;
-    int mesh = (int)(row / ((int64_t)P.nk * P.nj));
+    // (32-bit divisions: a 64-bit one is ~100 instructions, and a thread would make four)
+    const uint32_t rows_per_mesh = (uint32_t)P.nk * (uint32_t)P.nj;
+    const int mesh = mesh0 + (nrow < 0x7fffffffll ? (int)((uint32_t)row / rows_per_mesh) : (int)(row / rows_per_mesh));
+    const uint32_t rin = (uint32_t)(row - (int64_t)(mesh - mesh0) * rows_per_mesh);      // row inside the mesh: j + nj * k
     int64_t nvox = nvox_of(P), pw = (nvox + 31) / 32;
-    int64_t rbase = (row - (int64_t)mesh * P.nk * P.nj) * P.ni;           // node index of i = 0
+    int64_t rbase = (int64_t)rin * P.ni;                                  // node index of i = 0
     const KeyMap km = keymap_of(P);
     const u64* K = key + (int64_t)mesh * (bricked ? km.stride : nvox);
-    const int rj = (int)((row - (int64_t)mesh * P.nk * P.nj) % P.nj), rk = (int)((row - (int64_t)mesh * P.nk * P.nj) / P.nj);
+    const int rk = (int)(rin / (uint32_t)P.nj), rj = (int)(rin - (uint32_t)rk * (uint32_t)P.nj);
     const int kyz = ky(rj, km.sbj) + kz(rk, km.sbk);
     const uint32_t* par = parity + (int64_t)mesh * pw;
     const bool aligned = (P.ni & 31) == 0;
