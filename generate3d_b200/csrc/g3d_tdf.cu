@@ -936,15 +936,18 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                     K[n] = ((u64)__float_as_uint(phi) << 32) | (sweep_code(s) << kCodeShift) | (uint32_t)ct;
                     if (!CL) {
                         // stamp the node's own level in every direction (codes only grow and all writers of a sweep
-                        // write the same value)
+                        // write the same value). No first-pass sweep can skip a level (each has neighbours nobody has
+                        // looked at yet), so the stamps are only kept when this kernel runs second-pass sweeps too.
                         const int pi = base.x + di * (int)(pos & 1023u), pj = base.y + dj * (int)((pos >> 10) & 1023u), pk = base.z + dk * (int)(pos >> 20);
+                        if (s_end > 8) {
 #pragma unroll
-                        for (int dq = 0; dq < 8; ++dq) {
-                            int ei, ej, ek;
-                            sweep_dir(dq, ei, ej, ek);
-                            const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) +
-                                           (ek > 0 ? pk - 1 : nk - 2 - pk);
-                            s_dirty[dq * dstride + lv + 3] = code;
+                            for (int dq = 0; dq < 8; ++dq) {
+                                int ei, ej, ek;
+                                sweep_dir(dq, ei, ej, ek);
+                                const int lv = (ei > 0 ? pi - 1 : ni - 2 - pi) + (ej > 0 ? pj - 1 : nj - 2 - pj) +
+                                               (ek > 0 ? pk - 1 : nk - 2 - pk);
+                                s_dirty[dq * dstride + lv + 3] = code;
+                            }
                         }
                         if (Cm) {
                             const int p = pi + ni * (pj + nj * pk);
