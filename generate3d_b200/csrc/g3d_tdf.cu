@@ -19,8 +19,9 @@
 //  tdf_sweep     one CTA (or one thread-block cluster) / mesh, the 2 x 8 Gauss-Seidel sweeps (cpp:57-80,
 //                163-172). Within one sweep node (a,b,c) (sweep-relative) reads only nodes of smaller a+b+c,
 //                so the nodes of one anti-diagonal level are independent: 16 x (ni+nj+nk-5) synchronous
-//                wavefront steps instead of 16 x (n-1)^3 serial ones. See the kernel for the three exact
-//                shortcuts (duplicate candidates, unchanged neighbours, untouched levels).
+//                wavefront steps instead of 16 x (n-1)^3 serial ones. See the kernels for the exact shortcuts
+//                (duplicate candidates, unchanged / met neighbours, band-box flags, untouched levels; on grids
+//                of at most 65,536 nodes the second pass runs in tdf_sweep_bm_kernel: activity bits, speculation).
 //  tdf_finalize  one warp / grid row: running parity along i (cpp:174-182), x out_scale (main.cpp:119), and
 //                the fused epilogues the pipeline applies later on the CPU: |sdf| <= 1 occupancy
 //                (vox2mesh/main.cpp:92), clamp at trunc (dataset_loader.py:137-139), sign*log(|x|+1)
@@ -30,7 +31,7 @@
 //
 // HBM layout (workspace): tri records [T_total] 64 B; band boxes [T_total] 16 B; keys u64 per mesh in 4x4x4 bricks
 // (hi = phi bits, lo = sweep change code | band-box flags | closest_tri, see kTriBits; KeyMap); parity bits u32 [n_mesh, ceil(nvox/32)];
-// sweep order table (shared by all meshes).
+// sweep order table (shared by all meshes); small grids: 17 change bitmaps per mesh + one of the grid-face nodes.
 #include <cuda_fp16.h>
 #include <limits.h>
 #include <stdlib.h>
@@ -689,21 +690,27 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
 
 // ----------------------------------------------------------------- sweep ----
 // One CTA per mesh. Per level each thread owns one node and must replay, in the reference's
-// order, "if (d(node, closest_tri(nb)) < phi) take it" for its 7 upwind neighbours. Three
+// order, "if (d(node, closest_tri(nb)) < phi) take it" for its 7 upwind neighbours. A few
 // observations remove most of that work without changing a single bit of the result
 // (d is a pure function of (node, triangle) and phi only ever decreases, so a comparison
-// that failed once fails for ever):
+// that failed once fails for ever, and a pair that was evaluated -- or skipped because it was
+// known to fail -- leaves phi(node) <= d(node, triangle) behind for good):
 //   1. a candidate equal to the node's own triangle, or to an earlier candidate of the same
 //      visit, cannot pass the strict `<`;
 //   2. a neighbour whose closest_tri has not changed since this node last examined it (in an
-//      earlier sweep that had the same neighbour upwind) cannot pass either. The top 5 bits of a key's low word record the
-//      sweep in which each node last changed; s_prev[s][r] is the last earlier sweep in which
-//      slot r of sweep s pointed at the same absolute neighbour. The whole second pass of a
-//      converged field is skipped this way. Nodes on the grid boundary are not part of every
-//      sweep lattice, so they take no shortcut of this kind;
-//   3. the surviving (node, triangle) pairs are unevenly spread over the lanes, so each warp
+//      earlier sweep that had the same neighbour upwind) cannot pass either. The top 4 bits of a
+//      key's low word record the sweep in which each node last changed; s_thr[s][f][r] is the last
+//      earlier sweep in which slot r of sweep s pointed at the same absolute neighbour, for a node
+//      lying on the grid faces f (such a node is not part of every sweep's lattice);
+//   3. nor can a candidate equal to the triangle of ANY neighbour that falls under 2: the node met
+//      that triangle when it examined that neighbour (sweep_need_mask);
+//   4. a neighbour that still holds its band-init triangle, with this node inside that triangle's
+//      band box, counts as met too: the band init evaluated the pair (band_flags, sweep_candidates);
+//   5. the surviving (node, triangle) pairs are unevenly spread over the lanes, so each warp
 //      pushes them into a private shared-memory queue, evaluates the queue densely (one pair
 //      per lane), and the owners then replay the results in neighbour order.
+// tests/sweep_rules_model.c states 1-4 (and the speculation of tdf_sweep_bm_kernel) on the CPU and is checked
+// against the plain oracle without a GPU.
 constexpr int kSweepQueue = 32 * 7;                 // worst case per warp and round
 // (three rounds need a 196 KB shared-memory carve-out at 7 CTAs per SM and lose more L1 than they gain: 13.8 ms
 // against 12.5 with two and 13.0 with one)
