@@ -36,6 +36,7 @@
 #include <limits.h>
 #include <stdlib.h>
 #include <type_traits>
+#include <algorithm>
 
 #include "g3d_internal.h"
 #include "g3d_ptd.cuh"
@@ -64,15 +65,21 @@ struct TdfWs {
     int32_t*  level_start;  // [nlev + 1]
     uint32_t* chg;          // [n_mesh][17][act_words]: nodes changed under each code (sweep activity bitmaps), small grids only
     uint32_t* bnd;          // [act_words]: nodes on a grid face
+    uint32_t* gact;         // cluster sweeps: [n_mesh][act_words] activity bits, [n_mesh][nlev + 4] level counters, [n_mesh] changes
+    uint32_t* glvcnt;
+    int32_t*  gnchg;
     int       act_words;    // 0: the grid is too large for the sweep's activity bitmap
     size_t    bytes;
 };
 
-// the sweep keeps one bit per grid node in shared memory when that is at most 8 KB
-inline int act_words_of(const g3d_tdf_params& p)
+// The second-pass sweep kernel keeps one bit per grid node: in shared memory when that is at most 8 KB (grids of up to
+// 65,536 nodes, any batch), in global memory for the small batches of larger grids that sweep with one cluster per mesh.
+constexpr int kClusterMeshes = 37;              // launch_sweep gives a mesh a cluster only when n_mesh * 4 <= SMs (148)
+inline bool act_in_smem(const g3d_tdf_params& p) { return (int64_t)p.ni * p.nj * p.nk <= 65536; }
+inline int act_words_of(const g3d_tdf_params& p, int32_t n_mesh)
 {
     const int64_t nvox = (int64_t)p.ni * p.nj * p.nk;
-    return nvox <= 65536 ? (int)((nvox + 31) / 32) : 0;
+    return (act_in_smem(p) || (n_mesh <= kClusterMeshes && nvox < ((int64_t)1 << 31))) ? (int)((nvox + 31) / 32) : 0;
 }
 
 __host__ __device__ inline int64_t nvox_of(const g3d_tdf_params& p) { return (int64_t)p.ni * p.nj * p.nk; }
@@ -113,9 +120,13 @@ TdfWs carve(void* base, int32_t n_mesh, int64_t total_tris, const g3d_tdf_params
     w.parity = (uint32_t*)take((size_t)n_mesh * pw * 4);
     w.order = (uint32_t*)take((size_t)nsweep * 4);
     w.level_start = (int32_t*)take((size_t)(nlev_of(p) + 2) * 4);
-    w.act_words = act_words_of(p);
+    w.act_words = act_words_of(p, n_mesh);
     w.chg = (uint32_t*)take((size_t)n_mesh * 17 * w.act_words * 4);
     w.bnd = (uint32_t*)take((size_t)w.act_words * 4);
+    const bool gl = w.act_words > 0 && n_mesh <= kClusterMeshes;     // (also for small grids: tests force clusters onto them)
+    w.gact = (uint32_t*)take(gl ? (size_t)n_mesh * w.act_words * 4 : 0);
+    w.glvcnt = (uint32_t*)take(gl ? (size_t)n_mesh * (nlev_of(p) + 4) * 4 : 0);
+    w.gnchg = (int32_t*)take(gl ? (size_t)n_mesh * 4 : 0);
     w.bytes = off;
     return w;
 }
@@ -644,11 +655,14 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
                  uint32_t* __restrict__ bnd, int act_words)
 {
     // (the grid is (na+1) x (nb+1) x (nc+1) nodes) bit i + ni (j + nj k) of bnd: the node lies on a grid face
-    for (int w = threadIdx.x; w < act_words; w += blockDim.x) {
+    // (every CTA builds the small tables for itself and takes a share of the two big loops)
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < act_words; w += gridDim.x * blockDim.x) {
         uint32_t m = 0u;
+        const int p0 = 32 * w;
+        int i = p0 % (na + 1), r = p0 / (na + 1), j = r % (nb + 1), k = r / (nb + 1);
         for (int b = 0; b < 32; ++b) {
-            const int p = 32 * w + b, i = p % (na + 1), r = p / (na + 1), j = r % (nb + 1), k = r / (nb + 1);
             if (k <= nc && (i == 0 || i == na || j == 0 || j == nb || k == 0 || k == nc)) m |= 1u << b;
+            if (++i > na) { i = 0; if (++j > nb) { j = 0; ++k; } }
         }
         bnd[w] = m;
     }
@@ -670,16 +684,16 @@ tdf_order_kernel(int na, int nb, int nc, int nlev, uint32_t* __restrict__ order,
         acc = 0;
         for (int l = 0; l < nlev; ++l) {
             ls[l] = acc;
-            level_start[l] = acc;
+            if (blockIdx.x == 0) level_start[l] = acc;
             acc += Fx(l) - Fx(l - nc);
         }
         ls[nlev] = acc;
-        level_start[nlev] = acc;
+        if (blockIdx.x == 0) level_start[nlev] = acc;
     }
     __syncthreads();
     auto Fx = [&](int x) { return x < 0 ? 0 : F[min(x, nm - 1)]; };
     const int64_t n = (int64_t)na * nb * nc;
-    for (int64_t q = threadIdx.x; q < n; q += blockDim.x) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
         const int a = (int)(q % na), r = (int)(q / na);
         const int b = r % nb, c = r / nb;
         const int m = a + b, l = m + c;
@@ -956,10 +970,11 @@ tdf_sweep_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __rest
                                 s_dirty[dq * dstride + lv + 3] = code;
                             }
                         }
-                        if (Cm) {
-                            const int p = pi + ni * (pj + nj * pk);
-                            atomicOr(Cm + (s + 1) * act_words + (p >> 5), 1u << (p & 31));
-                        }
+                    }
+                    if (Cm) {
+                        const int pi = base.x + di * (int)(pos & 1023u), pj = base.y + dj * (int)((pos >> 10) & 1023u), pk = base.z + dk * (int)(pos >> 20);
+                        const int p = pi + ni * (pj + nj * pk);
+                        atomicOr(Cm + (s + 1) * act_words + (p >> 5), 1u << (p & 31));
                     }
                 }
             };
@@ -1063,18 +1078,22 @@ __device__ __noinline__ void sweep_init_bitmap(const uint32_t* Klo, KeyMap km, i
 // bitmaps of the codes above the slot's threshold; that union, shifted by the slot's offset in the linear index, marks the
 // nodes n. Interior nodes use their exact thresholds (thw: the seven bytes of s_thr[s][0]); nodes on a grid face, whose
 // thresholds are older, use the oldest one of the sweep (tmin). Shifts that run across a row end only set extra bits.
+template <bool CL>
 __device__ __noinline__ void sweep_build_activity(int s, int tmin, uint2 thw, const uint32_t* Cm, int act_words,
                                                   const uint32_t* __restrict__ bnd, uint32_t* s_act, int ni, int nj)
 {
     int di, dj, dk;
     sweep_dir(s, di, dj, dk);
-    for (int w = threadIdx.x; w < act_words; w += (int)blockDim.x) s_act[w] = 0u;
-    __syncthreads();
+    // (CL: the bitmap lives in global memory and the cluster's CTAs share the words)
+    const int t0 = (CL ? (int)cluster_ctarank() * (int)blockDim.x : 0) + (int)threadIdx.x;
+    const int tn = (CL ? (int)cluster_nctarank() : 1) * (int)blockDim.x;
+    for (int w = t0; w < act_words; w += tn) s_act[w] = 0u;
+    if (CL) cluster_barrier(); else __syncthreads();
     int th[7];
 #pragma unroll
     for (int r = 0; r < 7; ++r) th[r] = (int)(int8_t)((r < 4 ? thw.x : thw.y) >> (8 * (r & 3)));
     const int nc = s - tmin;                           // codes tmin + 1 .. s: at most 8 (first pass: s + 1; second: 7)
-    for (int w = threadIdx.x; w < act_words; w += (int)blockDim.x) {
+    for (int w = t0; w < act_words; w += tn) {
         uint32_t cw[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) cw[q] = q < nc ? __ldcg(Cm + (s - q) * act_words + w) : 0u;
@@ -1104,22 +1123,26 @@ __device__ __noinline__ void sweep_build_activity(int s, int tmin, uint2 thw, co
             }
         }
     }
-    __syncthreads();
+    if (CL) cluster_barrier(); else __syncthreads();
 }
 
-template <int NT>
+// CL: one mesh per thread-block cluster (large grids / small batches, second-pass sweeps only): the activity bitmap, the
+// level counters and the change count live in global memory, the CTAs share every loop and meet at cluster barriers.
+template <int NT, bool CL>
 __global__ void __launch_bounds__(NT, NT == 128 ? 7 : (NT == 256 ? 3 : 1))
 tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __restrict__ tri_off,
                     const uint32_t* __restrict__ order, const int32_t* __restrict__ level_start, int nlev,
                     int lev_words, g3d_tdf_params P, u64* counter, uint32_t* chg, const uint32_t* __restrict__ bnd,
-                    int act_words, int s_begin, int s_end, int spec_div)
+                    int act_words, int s_begin, int s_end, int spec_div, uint32_t* gact, uint32_t* glvcnt, int* gnchg)
 {
+    auto csync = [] { if (CL) cluster_barrier(); else __syncthreads(); };
+    const int csize = CL ? (int)cluster_nctarank() : 1, crank = CL ? (int)cluster_ctarank() : 0;
     u64 n_eval = 0;
     extern __shared__ uint32_t s_mem[];
     __shared__ __align__(8) int8_t s_thr[16][8][8];    // as in tdf_sweep_kernel
     __shared__ __align__(16) uint32_t s_thrw[8][8];
     __shared__ __align__(16) uint32_t s_ib[8];
-    __shared__ int s_nchg;                             // nodes changed in the sweep so far
+    __shared__ int s_nchg_cta;                         // nodes changed in the sweep so far (one CTA per mesh)
     int32_t* s_lev = reinterpret_cast<int32_t*>(s_mem);                         // [nlev + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -1128,8 +1151,11 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
     uint32_t* q_pos = q_tri + R * kSweepQueue;
     const int dstride = nlev + 3;
     uint8_t* s_dirty = reinterpret_cast<uint8_t*>(s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue));   // [8][nlev + 3]
-    uint32_t* s_act = s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue) + (8 * dstride + 3) / 4;        // [act_words]
-    uint32_t* s_lvcnt = s_act + act_words;             // [nlev + 4]: marked nodes per level (speculative sweeps)
+    const int mesh = blockIdx.x / csize;
+    uint32_t* s_act = CL ? gact + (size_t)mesh * act_words
+                         : s_mem + lev_words + (NT / 32) * (2 * R * kSweepQueue) + (8 * dstride + 3) / 4;               // [act_words]
+    uint32_t* s_lvcnt = CL ? glvcnt + (size_t)mesh * (nlev + 4) : s_act + act_words;   // [nlev + 4]: marked nodes per level (speculative sweeps)
+    int* const s_nchg = CL ? gnchg + mesh : &s_nchg_cta;
     uint32_t* s_list = q_tri;                          // the nodes waiting for a batch; the queue is idle while they collect
     for (int l = threadIdx.x; l <= nlev; l += NT) s_lev[l] = level_start[l];
     // (taking over from tdf_sweep_kernel after sweep s_begin - 1: its level stamps are gone, so a plain sweep here skips no level)
@@ -1148,8 +1174,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
         }
         s_thr[s][f][r] = (int8_t)thr;
     }
-    if (threadIdx.x == 0) s_nchg = s_begin ? 0 : 0x7fffffff;
-    const int mesh = blockIdx.x;
+    if (threadIdx.x == 0 && crank == 0) *s_nchg = s_begin ? 0 : 0x7fffffff;
     const KeyMap km = keymap_of(P);
     u64* K = key + (int64_t)mesh * km.stride;
     const uint32_t* Klo = (const uint32_t*)K;
@@ -1159,13 +1184,13 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
     const float rcp_ni = 1.0f / (float)ni, rcp_nj = 1.0f / (float)nj;
     // change bitmaps of this mesh, one per code (0 = the band init, s + 1 = sweep s), zero at launch
     uint32_t* Cm = chg + (int64_t)mesh * 17 * act_words;
-    __syncthreads();
-    if (s_begin == 0) {
+    csync();
+    if (s_begin == 0) {                             // (never with a cluster: those take over after the first pass)
         sweep_init_bitmap(Klo, km, ni, nj, nk, Cm, act_words);
     } else {                                        // the nodes sweep s_begin - 1 changed
         int c = 0;
-        for (int w = threadIdx.x; w < act_words; w += NT) c += __popc(__ldcg(Cm + s_begin * act_words + w));
-        if (c) atomicAdd(&s_nchg, c);
+        for (int w = crank * NT + threadIdx.x; w < act_words; w += NT * csize) c += __popc(__ldcg(Cm + s_begin * act_words + w));
+        if (c) atomicAdd(s_nchg, c);
     }
 
     // One sweep. SP = false: the plain level-synchronous sweep of tdf_sweep_kernel (every node of every level that is not
@@ -1177,14 +1202,14 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
         const int tmin = s_thr[s][7][6];            // the oldest threshold of the sweep: the last sweep in the same direction
         const volatile uint8_t* dirty = s_dirty + (s & 7) * dstride;
         if (SP) {
-            for (int l = threadIdx.x; l < nlev + 4; l += NT) s_lvcnt[l] = 0u;
+            for (int l = crank * NT + threadIdx.x; l < nlev + 4; l += NT * csize) s_lvcnt[l] = 0u;
             if (s <= 7) {
                 // first pass: each sweep brings neighbours no sweep has looked at before, so about every node that has a
                 // neighbour with a triangle is active: all bits on, no bitmap arithmetic
-                for (int w = threadIdx.x; w < act_words; w += NT) s_act[w] = 0xffffffffu;
-                __syncthreads();
+                for (int w = crank * NT + threadIdx.x; w < act_words; w += NT * csize) s_act[w] = 0xffffffffu;
+                csync();
             } else {
-                sweep_build_activity(s, tmin, *reinterpret_cast<const uint2*>(&s_thr[s][0][0]), Cm, act_words, bnd, s_act, ni, nj);
+                sweep_build_activity<CL>(s, tmin, *reinterpret_cast<const uint2*>(&s_thr[s][0][0]), Cm, act_words, bnd, s_act, ni, nj);
             }
         }
         uint32_t* const chg_code = Cm + (s + 1) * act_words;
@@ -1196,9 +1221,20 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
             if (flat) {
                 beg = 0; end = s_lev[nlev];
             } else {
-                if (SP) { if (((const volatile uint32_t*)s_lvcnt)[L] == 0u) continue; }   // no marked node on this level
+                if (SP) {
+                    // on to the next level that holds a marked node, 32 counters per look (a level-by-level look costs a
+                    // cluster a global-memory round trip per level)
+                    bool found = false;
+                    while (L < nlev) {
+                        const uint32_t c = L + lane < nlev ? ((const volatile uint32_t*)s_lvcnt)[L + lane] : 0u;
+                        const uint32_t m = __ballot_sync(0xffffffffu, c != 0u);
+                        if (m) { L += __ffs(m) - 1; found = true; break; }
+                        L += 32;
+                    }
+                    if (!found) break;
+                }
                 // nothing upwind of this whole level has changed since it was last examined
-                else if (max(max((int)dirty[L], (int)dirty[L + 1]), (int)dirty[L + 2]) <= tmin) continue;
+                else if (!CL && max(max((int)dirty[L], (int)dirty[L + 1]), (int)dirty[L + 2]) <= tmin) continue;
                 beg = s_lev[L]; end = s_lev[L + 1];
             }
             // node phase of one round: candidates of this lane's node go to the queue from slot `qbase` on; returns
@@ -1276,9 +1312,9 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                 }
             };
             int ln = 0;                                 // SP: nodes waiting in s_list (warp-uniform)
-            int fnext = warp * 32, fidx = 0;            // flat visit: next chunk of bitmap words, this lane's word
+            int fnext = (crank * (NT / 32) + warp) * 32, fidx = 0;            // flat visit: next chunk of bitmap words, this lane's word
             uint32_t fword = 0u;                        //             and what is left of it
-            for (int qb = beg + warp * 32; ; qb += R * NT) {
+            for (int qb = beg + crank * NT + warp * 32; ; qb += R * NT * csize) {
                 bool vA = false, vB = false, kp0 = false, kp1 = false;
                 uint32_t posA = 0, posB = 0, keep0 = 0, keep1 = 0;
                 auto node_at = [&](int q, uint32_t& pos) -> bool {
@@ -1291,7 +1327,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                     pos = (uint32_t)i | ((uint32_t)j << 10) | ((uint32_t)k << 20);
                     if (!SP) return true;
                     const int p = i + ni * (j + nj * k);
-                    return (s_act[p >> 5] >> (p & 31)) & 1u;
+                    return (((const volatile uint32_t*)s_act)[p >> 5] >> (p & 31)) & 1u;
                 };
                 if (SP) {
                     // scan R rounds against the activity bits. Where most nodes are active they go straight on; otherwise
@@ -1306,8 +1342,8 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                         if (!__any_sync(0xffffffffu, fword != 0u)) {
                             if (fnext < act_words) {
                                 fidx = fnext + lane;
-                                fword = fidx < act_words ? s_act[fidx] : 0u;
-                                fnext += NT;
+                                fword = fidx < act_words ? ((const volatile uint32_t*)s_act)[fidx] : 0u;
+                                fnext += NT * csize;
                                 continue;
                             }
                             more = false;
@@ -1331,7 +1367,7 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                         }
                     } else if (more) {
                         vA = node_at(qb + lane, posA);
-                        if (R == 2) vB = node_at(qb + NT + lane, posB);
+                        if (R == 2) vB = node_at(qb + NT * csize + lane, posB);
                         const uint32_t m0 = __ballot_sync(0xffffffffu, vA), m1 = R == 2 ? __ballot_sync(0xffffffffu, vB) : 0u;
                         const int c0 = __popc(m0), c1 = __popc(m1);
                         if (c0 + c1 == 0) continue;
@@ -1361,13 +1397,13 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                 } else {
                     if (qb >= end) break;
                     vA = node_at(qb + lane, posA);
-                    if (R == 2) vB = node_at(qb + NT + lane, posB);
+                    if (R == 2) vB = node_at(qb + NT * csize + lane, posB);
                 }
                 uint32_t needA, needB = 0;
                 float phiA, phiB = 0.f;
                 int ctA, nA, offA, ctB = -1, nB = 0, offB = 0;
                 int W = node_phase(vA, posA, 0, needA, phiA, ctA, nA, offA);
-                if (R == 2 && (SP ? __any_sync(0xffffffffu, vB) : qb + NT < end)) W += node_phase(vB, posB, W, needB, phiB, ctB, nB, offB);
+                if (R == 2 && (SP ? __any_sync(0xffffffffu, vB) : qb + NT * csize < end)) W += node_phase(vB, posB, W, needB, phiB, ctB, nB, offB);
                 if (W != 0) {
                     __syncwarp();
                     for (int e = lane; e < W; e += 32) {
@@ -1386,21 +1422,21 @@ tdf_sweep_bm_kernel(u64* key, const float4* __restrict__ tri, const int64_t* __r
                 if (SP && kp0) s_list[lane] = keep0;
                 if (SP && R == 2 && kp1) s_list[32 + lane] = keep1;
             }
-            __syncthreads();
+            csync();
         }
         }
-        if (n_changed) atomicAdd(&s_nchg, n_changed);
+        if (n_changed) atomicAdd(s_nchg, n_changed);
     };
 
     for (int s = s_begin; s < s_end; ++s) {
         // activity bits + speculation once the previous sweep changed few nodes (spec_div: tuning / test knob, 0 = never)
-        __syncthreads();
-        const int prev = s_nchg;
+        csync();
+        const int prev = *(volatile int*)s_nchg;
         // (spec_div < 0: always, from sweep 1 on -- tests)
         const bool spec = spec_div < 0 ? s >= 1 : (spec_div > 0 && s >= 8 && (int64_t)prev * spec_div <= (int64_t)n_lattice);
         sweep_threshold_words(s, s_thr[s], s_thrw, s_ib);
-        __syncthreads();
-        if (threadIdx.x == 0) s_nchg = 0;
+        csync();
+        if (threadIdx.x == 0 && crank == 0) *s_nchg = 0;
         if (spec) sweep(std::true_type(), s); else sweep(std::false_type(), s);
     }
     if (counter && n_eval) atomicAdd(counter + 1, n_eval);
@@ -1533,22 +1569,35 @@ int launch_sweep_nt(int n_mesh, int csize, int nlev, const TdfWs& w, const int64
     return G3D_OK;
 }
 
-// the small-grid kernel (activity bits + speculation), one CTA per mesh
-template <int NT>
-int launch_sweep_bm(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
+// the second-pass kernel (activity bits + speculation): one CTA per mesh with the bits in shared memory, or one cluster
+// per mesh with the bits in global memory
+template <int NT, bool CL>
+int launch_sweep_bm(int n_mesh, int csize, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
                     cudaStream_t stream, int s_begin)
 {
     const int lev_words = (nlev + 1 + 3) & ~3;
     const size_t smem = (size_t)(lev_words + (NT / 32) * 2 * sweep_rounds(NT) * kSweepQueue + (8 * (nlev + 3) + 3) / 4 +
-                                 w.act_words + nlev + 4) * 4;
-    auto kern = tdf_sweep_bm_kernel<NT>;
+                                 (CL ? 0 : w.act_words + nlev + 4)) * 4;
+    auto kern = tdf_sweep_bm_kernel<NT, CL>;
     G3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // speculate once a sweep changed at most 1/8 of the lattice nodes; G3D_SWEEP_SPEC overrides the divisor (0 = never)
     const char* e_sp = getenv("G3D_SWEEP_SPEC");
     const int spec_div = e_sp ? atoi(e_sp) : 8;
-    kern<<<(unsigned)n_mesh, NT, smem, stream>>>(w.key, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
-                                                 (const int32_t*)w.level_start, nlev, lev_words, p, cnt, w.chg,
-                                                 (const uint32_t*)w.bnd, w.act_words, s_begin, 16, spec_div);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_mesh * csize));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL ? 1 : 0;
+    G3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, w.key, (const float4*)w.tri, tri_off, (const uint32_t*)w.order,
+                                    (const int32_t*)w.level_start, nlev, lev_words, p, cnt, w.chg, (const uint32_t*)w.bnd,
+                                    w.act_words, s_begin, 16, spec_div, w.gact, w.glvcnt, (int*)w.gnchg));
     return G3D_OK;
 }
 
@@ -1560,7 +1609,7 @@ int sweep_two_kernels(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_o
         int rc = launch_sweep_nt<NT, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream, 0, split, w.chg);
         if (rc != G3D_OK) return rc;
     }
-    return split < 16 ? launch_sweep_bm<NT>(n_mesh, nlev, w, tri_off, p, cnt, stream, split) : G3D_OK;
+    return split < 16 ? launch_sweep_bm<NT, false>(n_mesh, 1, nlev, w, tri_off, p, cnt, stream, split) : G3D_OK;
 }
 
 int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, const g3d_tdf_params& p, u64* cnt,
@@ -1589,11 +1638,20 @@ int launch_sweep(int n_mesh, int nlev, const TdfWs& w, const int64_t* tri_off, c
     }
     if (forced) nt = forced;
     if (forced_cl) { csize = forced_cl; nt = 1024; }
-    if (csize > 1) return launch_sweep_nt<1024, true>(n_mesh, csize, nlev, w, tri_off, p, cnt, stream);
+    const char* e_bm = getenv("G3D_SWEEP_BITMAP");
+    const bool bm_off = e_bm && atoi(e_bm) == 0;
+    if (csize > 1) {
+        // a cluster per mesh: first pass in the plain kernel (recording its changes), second pass in the bitmap kernel
+        if (bm_off || w.act_words == 0 || n_mesh > kClusterMeshes)
+            return launch_sweep_nt<1024, true>(n_mesh, csize, nlev, w, tri_off, p, cnt, stream);
+        G3D_CUDA_TRY(cudaMemsetAsync(w.chg, 0, (size_t)n_mesh * 17 * w.act_words * 4, stream));
+        int rc = launch_sweep_nt<1024, true>(n_mesh, csize, nlev, w, tri_off, p, cnt, stream, 0, 8, w.chg);
+        if (rc != G3D_OK) return rc;
+        return launch_sweep_bm<1024, true>(n_mesh, csize, nlev, w, tri_off, p, cnt, stream, 8);
+    }
     // grids of at most 65,536 nodes: the kernel with one activity bit per node in shared memory; G3D_SWEEP_BITMAP=0 turns
     // it off (tests run both)
-    const char* e_bm = getenv("G3D_SWEEP_BITMAP");
-    const bool bm = w.act_words > 0 && !(e_bm && atoi(e_bm) == 0);
+    const bool bm = w.act_words > 0 && act_in_smem(p) && !bm_off;
     // first pass: the plain kernel, which also puts every change on record; second pass: the bitmap kernel. (G3D_SWEEP_SPLIT:
     // the sweep at which it takes over, 0 = from the start -- tests and tuning.)
     const char* e_split = getenv("G3D_SWEEP_SPLIT");
@@ -1787,7 +1845,9 @@ int tdf_solve(const int64_t* tri_off, int64_t total_tris, int32_t n_mesh, const 
         const int nlev = nlev_of(p);
         if (total_tris > 0 && nlev > 0) {
             size_t smem = (size_t)(nlev + 1 + (p.ni - 1) + (p.nj - 1) - 1) * 4;
-            tdf_order_kernel<<<1, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start, w.bnd, w.act_words);
+            const int64_t n_lat = (int64_t)(p.ni - 1) * (p.nj - 1) * (p.nk - 1);
+            const unsigned ob = (unsigned)std::min<int64_t>(std::max<int64_t>(n_lat / 16384, 1), 64);     // 16 entries per thread and more
+            tdf_order_kernel<<<ob, 1024, smem, stream>>>(p.ni - 1, p.nj - 1, p.nk - 1, nlev, w.order, w.level_start, w.bnd, w.act_words);
             prof_mark(ST_ORDER, stream);
             int rc = launch_sweep(n_mesh, nlev, w, tri_off, p, cnt, stream);
             if (rc != G3D_OK) return rc;

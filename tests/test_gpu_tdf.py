@@ -519,17 +519,23 @@ def config3_case(oracle):
     return v, t, phi * np.float32(128)
 
 
-@pytest.mark.parametrize("cluster", [None, "2", "4", "8"])
+@pytest.mark.parametrize("cluster", [None, "2", "4", "8", "8-plain", "4-spec"])
 def test_config3_128cube_200k_tris_faithful_bit_equal(g3d, oracle, config3_case, cluster, monkeypatch):
     """configs[3] (128^3 x 201,840 triangles), faithful mode, bit-equal to the reference's make_level_set3 with the
-    sweep's thread-block cluster size left to the library and forced to 2, 4 and 8 CTAs per mesh."""
+    sweep's thread-block cluster size left to the library and forced to 2, 4 and 8 CTAs per mesh (second pass in the
+    cluster form of the bitmap kernel, activity bits in global memory), with all 16 sweeps in the plain cluster kernel
+    ("8-plain") and with speculation forced in every second-pass sweep ("4-spec")."""
     from generate3d_b200 import dfgen
     v, t, want = config3_case
     assert len(t) == 201840
-    if cluster is None:
-        monkeypatch.delenv("G3D_SWEEP_CLUSTER", raising=False)
-    else:
-        monkeypatch.setenv("G3D_SWEEP_CLUSTER", cluster)
+    for k in ("G3D_SWEEP_CLUSTER", "G3D_SWEEP_BITMAP", "G3D_SWEEP_SPEC"):
+        monkeypatch.delenv(k, raising=False)
+    if cluster is not None:
+        monkeypatch.setenv("G3D_SWEEP_CLUSTER", cluster.split("-")[0])
+        if cluster.endswith("-plain"):
+            monkeypatch.setenv("G3D_SWEEP_BITMAP", "0")
+        if cluster.endswith("-spec"):
+            monkeypatch.setenv("G3D_SWEEP_SPEC", "-1")
     got = _run(dfgen, [(v, t)], 128, outputs=("sdf", "occ_f32", "status"))
     assert got["status"][0] == 0
     assert np.array_equal(_bits(got["sdf"][0]), _bits(want))
