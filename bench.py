@@ -330,8 +330,8 @@ def bench_other_configs(args, rank, world, dev, barrier, peak_tf, nominal_tf):
                                        "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
                                        "frac_of_nominal": ach / nominal_tf, "evals_per_launch": dom_evals,
                                        "kernel_ms": st.get(dom), "traffic": None}}
-            # faithful: fill, prep, band init, order, sweep (two kernels on grids the small-grid kernel takes), finalize
-            launches += (7 if (mode == "exact" or dim ** 3 <= 65536) else 6) * (steps + warm + 1)
+            # faithful: fill, prep, band init (+ flags after the scatter kernel), order, two sweep kernels, finalize
+            launches += 7 * (steps + warm + 1)
             keep[mode] = o["sdf"][0].clone()
             assert int(o["status"].sum().item()) == 0
         return case, (v, t, keep)
