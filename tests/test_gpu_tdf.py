@@ -519,10 +519,10 @@ def config3_case(oracle):
     return v, t, phi * np.float32(128)
 
 
-@pytest.mark.parametrize("cluster", [None, "2", "4", "8", "8-plain", "4-spec"])
+@pytest.mark.parametrize("cluster", [None, "2", "4", "8", "16", "8-plain", "4-spec"])
 def test_config3_128cube_200k_tris_faithful_bit_equal(g3d, oracle, config3_case, cluster, monkeypatch):
     """configs[3] (128^3 x 201,840 triangles), faithful mode, bit-equal to the reference's make_level_set3 with the
-    sweep's thread-block cluster size left to the library and forced to 2, 4 and 8 CTAs per mesh (second pass in the
+    sweep's thread-block cluster size left to the library (16) and forced to 2, 4, 8 and 16 CTAs per mesh (second pass in the
     cluster form of the bitmap kernel, activity bits in global memory), with all 16 sweeps in the plain cluster kernel
     ("8-plain") and with speculation forced in every second-pass sweep ("4-spec")."""
     from generate3d_b200 import dfgen
